@@ -1,0 +1,241 @@
+/*
+ * lighthand_b200.h -- C ABI of liblighthand_b200.so (sm_100a).
+ *
+ * B200-native implementation of the LightHand heatmap pipeline
+ *     crop/warp + normalise -> Gaussian targets -> JointsMSELoss fwd/bwd -> argmax decode -> PCK/AUC/EPE
+ * The reference (leejeongho3214/LightHand) is pure Python and has no FFI; the interface each
+ * entry point replaces is the Python function cited next to it (paths relative to the reference
+ * repo root).  INTEGRATION.md shows the ctypes binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - Plain C: pointers, sizes, scalars, two POD structs.  No torch / C++ types.
+ *   - "dev" pointers are device pointers owned by the caller; nothing is allocated or freed by
+ *     the lh_* kernels entry points (the lh_pipeline_* context owns its own buffers).
+ *   - Every kernel entry point is asynchronous on `stream` (a cudaStream_t passed as void*).
+ *   - Return value: 0 success; <0 argument error (LH_E*); >0 a cudaError_t from the launch.
+ *   - Re-entrant; no global mutable state; safe from several host threads on distinct streams.
+ *   - There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef LIGHTHAND_B200_H
+#define LIGHTHAND_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LH_ABI_VERSION 1
+
+#define LH_OK            0
+#define LH_EINVAL       (-1)  /* bad size / enum value */
+#define LH_ENULL        (-2)  /* required pointer is NULL */
+#define LH_EALIGN       (-3)  /* pointer / pitch alignment requirement not met */
+#define LH_EUNSUPPORTED (-4)  /* geometry outside what the kernels implement */
+#define LH_ENOMEM       (-5)  /* workspace too small / allocation failed (pipeline ctx) */
+#define LH_ENODEVICE    (-6)  /* no sm_100 device */
+
+typedef void* lh_stream_t; /* cudaStream_t */
+
+int lh_abi_version(void);
+const char* lh_strerror(int code);
+/* device properties the host side needs for grid sizing / reporting */
+int lh_device_query(int device, int* sm_count, int* cc_major, int* cc_minor, uint64_t* total_mem);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  warp + normalise.
+ * Replaces: generate_patch_image            src/utils/preprocessing.py:144-162
+ *           (cv2.warpAffine INTER_LINEAR, BORDER_CONSTANT 0; flip src/utils/preprocessing.py:153-155)
+ *           colour gain + clip              src/utils/preprocessing.py:81
+ *           ToTensor / Resize / Normalize   src/tools/dataset.py:147-157
+ * ------------------------------------------------------------------------------------------ */
+#define LH_INTERP_CV2_U8   0 /* cv2 fixed-point grid, uint8 rounding ((sum p*w + 2^14)>>15)     */
+#define LH_INTERP_CV2_F32  1 /* cv2 fixed-point grid, float32 weights (reference feeds float32) */
+#define LH_INTERP_TORCH    2 /* torch bilinear resize, align_corners=False, edge clamp          */
+#define LH_CHAN_RGB 0
+#define LH_CHAN_BGR 1        /* src/datasets/frei_dataloader.py:338 returns channels (2,1,0)    */
+#define LH_LAYOUT_CHW 0      /* network input  [N,3,out_h,out_w]                                */
+#define LH_LAYOUT_HWC 1      /* image patch    [N,out_h,out_w,3]  (generate_patch_image result) */
+
+/* Normalisation table for LH_INTERP_CV2_U8: lut[i][c][v] = ((clip(v*gain[i][c],0,255))/255 - mean[c])/std[c]
+ * evaluated with IEEE float32/float64 ops in torch's order (bit-exact).  chan_gain dev [N,3] double or
+ * NULL (then one table, N ignored).  mean_std host [6] = mean[3],std[3]; NULL -> identity table
+ * (value 0..255 after gain/clip, no /255).  lut dev [(chan_gain?N:1)][3][256] float. */
+int lh_norm_lut_build(const double* chan_gain, int N, const float* mean_std, float* lut, lh_stream_t stream);
+
+int lh_warp_normalize(const uint8_t* src,        /* dev N HWC RGB uint8 images                   */
+                      int64_t src_img_stride,    /* bytes between images                          */
+                      int src_h, int src_w, int src_pitch /* bytes per row */,
+                      const double* fwd_affine,  /* dev [N,2,3] src->dst as cv2.warpAffine takes it; unused for LH_INTERP_TORCH */
+                      const uint8_t* flip,       /* dev [N] 0/1 or NULL                           */
+                      const double* chan_gain,   /* dev [N,3] or NULL                             */
+                      const float* mean_std,     /* host [6] or NULL (identity)                   */
+                      const float* lut,          /* dev table from lh_norm_lut_build (CV2_U8 only)*/
+                      int interp, int chan_order, int out_layout,
+                      float* dst, int N, int out_h, int out_w, lh_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  Gaussian targets.
+ * Replaces: CustomDataset.generate_target   src/tools/dataset.py:165-212  (style 0)
+ *           GenerateHeatmap.__call__        src/utils/dataset_loader.py:22-53 (style 1; input = joints/4)
+ * gauss_table: dev side*side float32, computed by the caller exactly as the reference does with
+ * numpy (bit-exact targets).  style 0: side = 2*tmp+1.  style 1: side = 6*sigma+3, sigma = H/64 integer.
+ * target_weight dev [N,J] or NULL.
+ * ------------------------------------------------------------------------------------------ */
+#define LH_TARGET_HRNET     0
+#define LH_TARGET_HOURGLASS 1
+int lh_gen_targets(const float* joints, int joint_stride /*floats per joint: 2 or 3*/,
+                   int N, int J, int H, int W, float stride_x, float stride_y,
+                   int style, const float* gauss_table, int table_side,
+                   float* target, float* target_weight, lh_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3  JointsMSELoss forward + backward.   Replaces src/utils/loss.py:306-325 (+ autograd backward).
+ * loss = 0.5/(N*J*HW) * sum((pred*w - target*w)^2), w = weight[n,j] or 1 (the reference ignores
+ * target_weight: pass NULL).  grad (nullable) = d loss / d pred.  loss_f64 / loss_f32: dev [1], nullable.
+ * ws: dev workspace of lh_heatmap_ws_bytes(N,J) bytes, zero-initialised ONCE by the caller (the
+ * kernels leave it zeroed again).
+ * ------------------------------------------------------------------------------------------ */
+size_t lh_heatmap_ws_bytes(int64_t N, int J);
+int lh_jmse_loss(const float* pred, const float* target, const float* weight,
+                 int64_t N, int J, int H, int W,
+                 double* loss_f64, float* loss_f32, float* grad,
+                 void* ws, lh_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4  decode.   Replaces get_max_preds src/utils/loss.py:327-355 and the callers' "* 4"
+ * (src/utils/method.py:173-178).  First-index tie-break, NaN counts as maximum, coordinates zeroed
+ * where maxval <= 0.  subpixel / inv_affine: upstream-HRNet quarter-pixel shift and inverse crop
+ * matrix (not in the reference; see oracle.restate.decode_final).
+ * coords dev [N,J,2]; maxvals dev [N,J] (nullable); argidx dev [N,J] int32 (nullable).
+ * ------------------------------------------------------------------------------------------ */
+int lh_decode(const float* heat, int64_t N, int J, int H, int W, float out_scale, int subpixel,
+              const double* inv_affine /*dev [N,2,3] or NULL*/,
+              float* coords, float* maxvals, int32_t* argidx, lh_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2+K3+K4 fused post-backbone pass: pred is read ONCE; target is generated on the fly from the
+ * joints (and written if `target` != NULL), loss/grad and decode come out of the same pass.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct lh_heatmap_args {
+    const float* pred;          /* dev [N,J,H,W]                                           */
+    const float* joints;        /* dev [N,J,joint_stride]  (input-image pixel coordinates) */
+    const float* gauss_table;   /* dev side*side                                           */
+    const float* target_in;     /* dev [N,J,H,W] or NULL; if set, used instead of joints   */
+    const double* inv_affine;   /* dev [N,2,3] or NULL                                     */
+    float* target_out;          /* dev [N,J,H,W] or NULL                                   */
+    float* target_weight_out;   /* dev [N,J] or NULL                                       */
+    float* grad;                /* dev [N,J,H,W] or NULL                                   */
+    double* loss_f64;           /* dev [1] or NULL                                         */
+    double* loss_meter;         /* dev [2] or NULL: += {loss*N, N}  (AverageMeter.update)  */
+    float* loss_f32;            /* dev [1] or NULL                                         */
+    float* coords;              /* dev [N,J,2] or NULL (no decode)                         */
+    float* maxvals;             /* dev [N,J] or NULL                                       */
+    int32_t* argidx;            /* dev [N,J] or NULL                                       */
+    void* ws;                   /* dev workspace, lh_heatmap_ws_bytes(N,J)                 */
+    int64_t N;
+    int32_t J, H, W;
+    int32_t joint_stride;
+    int32_t table_side;
+    int32_t style;              /* LH_TARGET_*                                             */
+    int32_t use_target_weight;  /* 0 = reference behaviour (weight ignored by the loss)    */
+    int32_t subpixel;
+    float stride_x, stride_y;
+    float out_scale;
+} lh_heatmap_args;
+int lh_heatmap_fused(const lh_heatmap_args* args, lh_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K5  metrics.
+ * lh_pck_epe_batch replaces PCK_2d_loss / PCK_2d_loss_visible (src/utils/loss.py:83-148) and
+ * EPE_train / EPE (src/utils/loss.py:28-67) for one batch; results ACCUMULATE into
+ *   counts dev u64[4] = { n_wrong (d > T), n_total, epe_count, n_images }
+ *   sums   dev f64[4] = { epe_sum, sum(loss_b * n_b), sum(n_b), reserved }   ([1],[2] via lh_heatmap_args.loss_meter)
+ * so a whole epoch needs one device->host read (AverageMeter, src/utils/metric_logger.py:7-28);
+ * PCK average = (n_total - n_wrong) / n_total, EPE average = epe_sum / epe_count.
+ * thr_f32: the threshold already rounded the way torch does it: (float)T for 'proportion',
+ * (float)(T*3.78) for 'mm'.
+ * ------------------------------------------------------------------------------------------ */
+#define LH_PCK_PROPORTION 0
+#define LH_PCK_MM         1
+int lh_pck_epe_batch(const float* pred_xy /*dev [N,J,2]*/, const float* gt /*dev [N,J,gt_stride]*/, int gt_stride,
+                     int64_t N, int J, float thr_f32, int mode, int visible,
+                     unsigned long long* counts, double* sums, lh_stream_t stream);
+
+/* lh_pck_curve_accum replaces the counting core of pred_eval / pred_test
+ * (src/utils/argparser.py:326-438): float64 distances, strict '<', per-category histograms.
+ *   thr_sorted dev f64[K] ascending.  hist dev u64[n_cat][K+1]: bin k counts distances whose first
+ *   satisfied threshold is k (bin K: none / NaN) -- count(d < thr[k]) = prefix sum.
+ *   n_valid dev u64[n_cat] (joints passing the visibility mask), n_all dev u64[n_cat] (all joints),
+ *   sum_d dev f64[n_cat] (pixel distance over ALL joints, the EPE numerator).
+ *   bbox_diag dev f32[N] or NULL (then computed as pred_store does, src/utils/argparser.py:268-272).
+ *   category dev i32[N] or NULL (all 0).  method 0 = pixels/mm thresholds, 1 = pckb (d / bbox).
+ *   use_vis: keep joints whose gt[..., gt_stride-1] == 1 (pred_eval) or all joints (pred_test). */
+int lh_pck_curve_accum(const float* pred_xy, const float* gt, int gt_stride,
+                       const float* bbox_diag, const int32_t* category, int n_cat,
+                       int64_t N, int J, const double* thr_sorted, int K, int method, int use_vis,
+                       unsigned long long* hist, unsigned long long* n_valid,
+                       unsigned long long* n_all, double* sum_d, lh_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-buffer pipeline context (what a non-torch host binds; also the e2e benchmark path).
+ * Owns device buffers, pinned staging, two streams and a CUDA graph of
+ *   H2D -> K1 -> fused(K2,K3,K4) -> K5 -> D2H.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct lh_pipeline_cfg {
+    int32_t device;
+    int32_t batch;              /* N */
+    int32_t src_h, src_w;       /* uint8 RGB HWC source size */
+    int32_t out_h, out_w;       /* network input size */
+    int32_t J, H, W;            /* joints, heat-map size */
+    int32_t interp;             /* LH_INTERP_* */
+    int32_t train;              /* 1: write grad */
+    int32_t materialize_target; /* 1: write the target heat-maps (what the reference's dataset returns) */
+    int32_t subpixel;
+    float sigma;
+    float pck_T;                /* in-loop PCK threshold, 'proportion' (src/utils/method.py:243) */
+    float mean_std[6];
+} lh_pipeline_cfg;
+typedef struct lh_pipeline lh_pipeline;
+
+typedef struct lh_pipeline_io {
+    /* host inputs (pageable or pinned) */
+    const uint8_t* images;      /* [N,src_h,src_w,3] */
+    const double* fwd_affine;   /* [N,2,3] */
+    const uint8_t* flip;        /* [N] or NULL */
+    const float* joints;        /* [N,J,2] ground truth in network-input pixels */
+    const float* pred;          /* host [N,J,H,W] or NULL: use the device-resident pred (lh_pipeline_pred_dev) */
+    /* host outputs (nullable) */
+    float* loss;                /* [1] */
+    float* coords;              /* [N,J,2] */
+    float* maxvals;             /* [N,J] */
+    unsigned long long* counts; /* [4] running totals, see lh_pck_epe_batch */
+    double* sums;               /* [4] */
+} lh_pipeline_io;
+
+int lh_pipeline_create(const lh_pipeline_cfg* cfg, const float* gauss_table_host, int table_side, lh_pipeline** out);
+void lh_pipeline_destroy(lh_pipeline* p);
+/* device-resident buffers of the context (backbone input / output live here) */
+float* lh_pipeline_input_dev(lh_pipeline* p);   /* [N,3,out_h,out_w] normalised images  */
+float* lh_pipeline_pred_dev(lh_pipeline* p);    /* [N,J,H,W] where the backbone writes   */
+float* lh_pipeline_grad_dev(lh_pipeline* p);    /* [N,J,H,W] d loss / d pred             */
+float* lh_pipeline_target_dev(lh_pipeline* p);  /* [N,J,H,W] or NULL                     */
+/* one step from host buffers: copies in, runs the kernels, copies results out, returns after the
+ * outputs are valid (synchronous w.r.t. the host). */
+int lh_pipeline_step_host(lh_pipeline* p, const lh_pipeline_io* io);
+/* asynchronous pair (two slots, double-buffered): submit step i+1 before waiting for step i so its
+ * host->device copy overlaps step i's kernels.  The io pointers must stay valid until the wait. */
+int lh_pipeline_submit(lh_pipeline* p, const lh_pipeline_io* io, int* slot_out);
+int lh_pipeline_wait(lh_pipeline* p, int slot);
+int lh_pipeline_reset_metrics(lh_pipeline* p);
+/* number of kernel launches one step issues (for accounting) */
+int lh_pipeline_launches_per_step(const lh_pipeline* p);
+/* pinned host memory so the copies above run at full DMA rate */
+void* lh_host_alloc(size_t bytes);
+void lh_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIGHTHAND_B200_H */

@@ -1,0 +1,246 @@
+// Host-buffer pipeline context: what a host without torch binds, and the end-to-end path
+// (host u8 images + matrices + joints in, loss / coordinates / metric counts out).
+//
+// Two slots are double-buffered so the H2D copy of step i+1 (copy stream, DMA engine) overlaps
+// the kernels of step i (compute stream); ordering is by CUDA events only, the host blocks once
+// per step on the slot's "done" event.  Kernels per step: K1 warp+normalise, fused K2+K3+K4,
+// K5 metrics (3 launches; the normalisation table is built once at create time).
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "lh_common.cuh"
+
+namespace {
+
+constexpr int kSlots = 2;
+
+struct Slot {
+    uint8_t* d_images = nullptr;
+    double* d_affine = nullptr;
+    uint8_t* d_flip = nullptr;
+    float* d_joints = nullptr;
+    float* d_coords = nullptr;
+    float* d_maxvals = nullptr;
+    float* d_loss = nullptr;
+    // pinned result block: loss[1] | coords[N*J*2] | maxvals[N*J] | counts u64[4] | sums f64[4]
+    unsigned char* h_out = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_done = nullptr;
+    bool busy = false;
+    lh_pipeline_io io{};
+};
+
+}  // namespace
+
+struct lh_pipeline {
+    lh_pipeline_cfg cfg{};
+    int table_side = 0;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    Slot slot[kSlots];
+    float* d_input = nullptr;
+    float* d_pred = nullptr;
+    float* d_target = nullptr;
+    float* d_grad = nullptr;
+    float* d_table = nullptr;
+    float* d_lut = nullptr;
+    void* d_ws = nullptr;
+    unsigned long long* d_counts = nullptr;
+    double* d_sums = nullptr;
+    size_t out_bytes = 0, off_coords = 0, off_maxvals = 0, off_counts = 0, off_sums = 0;
+    unsigned long long step = 0;
+};
+
+#define PCHK(x)                                      \
+    do {                                             \
+        cudaError_t e__ = (x);                       \
+        if (e__ != cudaSuccess) { rc = (int)e__; goto fail; } \
+    } while (0)
+
+extern "C" void lh_pipeline_destroy(lh_pipeline* p) {
+    if (!p) return;
+    cudaSetDevice(p->cfg.device);
+    if (p->s_comp) cudaStreamSynchronize(p->s_comp);
+    if (p->s_copy) cudaStreamSynchronize(p->s_copy);
+    for (auto& s : p->slot) {
+        cudaFree(s.d_images); cudaFree(s.d_affine); cudaFree(s.d_flip); cudaFree(s.d_joints);
+        cudaFree(s.d_coords); cudaFree(s.d_maxvals); cudaFree(s.d_loss);
+        if (s.h_out) cudaFreeHost(s.h_out);
+        if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+        if (s.ev_done) cudaEventDestroy(s.ev_done);
+    }
+    cudaFree(p->d_input); cudaFree(p->d_pred); cudaFree(p->d_target); cudaFree(p->d_grad);
+    cudaFree(p->d_table); cudaFree(p->d_lut); cudaFree(p->d_ws); cudaFree(p->d_counts); cudaFree(p->d_sums);
+    if (p->s_copy) cudaStreamDestroy(p->s_copy);
+    if (p->s_comp) cudaStreamDestroy(p->s_comp);
+    delete p;
+}
+
+extern "C" int lh_pipeline_create(const lh_pipeline_cfg* cfg, const float* table_host, int table_side,
+                                  lh_pipeline** out) {
+    if (!cfg || !table_host || !out) return LH_ENULL;
+    if (cfg->batch <= 0 || cfg->src_h <= 0 || cfg->src_w <= 0 || cfg->out_h <= 0 || cfg->out_w <= 0 ||
+        cfg->J <= 0 || cfg->H <= 0 || cfg->W <= 0 || table_side < 1 || (table_side & 1) == 0 || table_side > 31)
+        return LH_EINVAL;
+    if (cfg->interp < LH_INTERP_CV2_U8 || cfg->interp > LH_INTERP_TORCH) return LH_EINVAL;
+    int rc = LH_OK;
+    lh_pipeline* p = new (std::nothrow) lh_pipeline();
+    if (!p) return LH_ENOMEM;
+    p->cfg = *cfg;
+    p->table_side = table_side;
+    const size_t N = cfg->batch, J = cfg->J, HW = (size_t)cfg->H * cfg->W;
+    const size_t img_bytes = (size_t)cfg->src_h * cfg->src_w * 3;
+    PCHK(cudaSetDevice(cfg->device));
+    PCHK(cudaStreamCreateWithFlags(&p->s_copy, cudaStreamNonBlocking));
+    PCHK(cudaStreamCreateWithFlags(&p->s_comp, cudaStreamNonBlocking));
+    p->off_coords = 16;
+    p->off_maxvals = p->off_coords + N * J * 2 * sizeof(float);
+    p->off_counts = (p->off_maxvals + N * J * sizeof(float) + 15) & ~(size_t)15;
+    p->off_sums = p->off_counts + 4 * sizeof(unsigned long long);
+    p->out_bytes = p->off_sums + 4 * sizeof(double);
+    for (auto& s : p->slot) {
+        PCHK(cudaMalloc(&s.d_images, N * img_bytes));
+        PCHK(cudaMalloc(&s.d_affine, N * 6 * sizeof(double)));
+        PCHK(cudaMalloc(&s.d_flip, N));
+        PCHK(cudaMemset(s.d_flip, 0, N));
+        PCHK(cudaMalloc(&s.d_joints, N * J * 2 * sizeof(float)));
+        PCHK(cudaMalloc(&s.d_coords, N * J * 2 * sizeof(float)));
+        PCHK(cudaMalloc(&s.d_maxvals, N * J * sizeof(float)));
+        PCHK(cudaMalloc(&s.d_loss, 16));
+        PCHK(cudaMallocHost(&s.h_out, p->out_bytes));
+        PCHK(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+        PCHK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    }
+    PCHK(cudaMalloc(&p->d_input, N * 3 * (size_t)cfg->out_h * cfg->out_w * sizeof(float)));
+    PCHK(cudaMalloc(&p->d_pred, N * J * HW * sizeof(float)));
+    PCHK(cudaMemset(p->d_pred, 0, N * J * HW * sizeof(float)));
+    if (cfg->materialize_target) PCHK(cudaMalloc(&p->d_target, N * J * HW * sizeof(float)));
+    if (cfg->train) PCHK(cudaMalloc(&p->d_grad, N * J * HW * sizeof(float)));
+    PCHK(cudaMalloc(&p->d_table, (size_t)table_side * table_side * sizeof(float)));
+    PCHK(cudaMemcpy(p->d_table, table_host, (size_t)table_side * table_side * sizeof(float), cudaMemcpyHostToDevice));
+    PCHK(cudaMalloc(&p->d_lut, 768 * sizeof(float)));
+    {
+        const size_t wsb = lh_heatmap_ws_bytes((int64_t)N, (int)J);
+        PCHK(cudaMalloc(&p->d_ws, wsb));
+        PCHK(cudaMemset(p->d_ws, 0, wsb));
+    }
+    PCHK(cudaMalloc(&p->d_counts, 4 * sizeof(unsigned long long)));
+    PCHK(cudaMalloc(&p->d_sums, 4 * sizeof(double)));
+    PCHK(cudaMemset(p->d_counts, 0, 4 * sizeof(unsigned long long)));
+    PCHK(cudaMemset(p->d_sums, 0, 4 * sizeof(double)));
+    rc = lh_norm_lut_build(nullptr, 1, cfg->mean_std, p->d_lut, p->s_comp);
+    if (rc) goto fail;
+    PCHK(cudaStreamSynchronize(p->s_comp));
+    *out = p;
+    return LH_OK;
+fail:
+    lh_pipeline_destroy(p);
+    return rc;
+}
+
+extern "C" float* lh_pipeline_input_dev(lh_pipeline* p) { return p ? p->d_input : nullptr; }
+extern "C" float* lh_pipeline_pred_dev(lh_pipeline* p) { return p ? p->d_pred : nullptr; }
+extern "C" float* lh_pipeline_grad_dev(lh_pipeline* p) { return p ? p->d_grad : nullptr; }
+extern "C" float* lh_pipeline_target_dev(lh_pipeline* p) { return p ? p->d_target : nullptr; }
+extern "C" int lh_pipeline_launches_per_step(const lh_pipeline*) { return 3; }
+
+extern "C" int lh_pipeline_reset_metrics(lh_pipeline* p) {
+    if (!p) return LH_ENULL;
+    cudaSetDevice(p->cfg.device);
+    cudaError_t e = cudaMemsetAsync(p->d_counts, 0, 4 * sizeof(unsigned long long), p->s_comp);
+    if (e == cudaSuccess) e = cudaMemsetAsync(p->d_sums, 0, 4 * sizeof(double), p->s_comp);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->s_comp);
+    return (int)e;
+}
+
+// enqueue one step into slot (step % 2) and report the slot through *slot_out
+extern "C" int lh_pipeline_submit(lh_pipeline* p, const lh_pipeline_io* io, int* slot_out) {
+    if (!p || !io || !io->images || !io->joints || !slot_out) return LH_ENULL;
+    const lh_pipeline_cfg& c = p->cfg;
+    if (c.interp != LH_INTERP_TORCH && !io->fwd_affine) return LH_ENULL;
+    const int si = (int)(p->step % kSlots);
+    Slot& s = p->slot[si];
+    if (s.busy) return LH_EINVAL;  // caller must lh_pipeline_wait() the slot first
+    const size_t N = c.batch, J = c.J, HW = (size_t)c.H * c.W;
+    const size_t img_bytes = (size_t)c.src_h * c.src_w * 3;
+    int rc = LH_OK;
+    PCHK(cudaSetDevice(c.device));
+    // H2D on the copy stream (the slot's previous consumer finished: its ev_done was waited by the host)
+    PCHK(cudaMemcpyAsync(s.d_images, io->images, N * img_bytes, cudaMemcpyHostToDevice, p->s_copy));
+    if (io->fwd_affine) PCHK(cudaMemcpyAsync(s.d_affine, io->fwd_affine, N * 6 * sizeof(double), cudaMemcpyHostToDevice, p->s_copy));
+    if (io->flip) PCHK(cudaMemcpyAsync(s.d_flip, io->flip, N, cudaMemcpyHostToDevice, p->s_copy));
+    PCHK(cudaMemcpyAsync(s.d_joints, io->joints, N * J * 2 * sizeof(float), cudaMemcpyHostToDevice, p->s_copy));
+    if (io->pred) {
+        // d_pred is shared by both slots: the copy must not overtake the previous step's kernels
+        if (p->step > 0) PCHK(cudaStreamWaitEvent(p->s_copy, p->slot[(si + kSlots - 1) % kSlots].ev_done, 0));
+        PCHK(cudaMemcpyAsync(p->d_pred, io->pred, N * J * HW * sizeof(float), cudaMemcpyHostToDevice, p->s_copy));
+    }
+    PCHK(cudaEventRecord(s.ev_h2d, p->s_copy));
+    PCHK(cudaStreamWaitEvent(p->s_comp, s.ev_h2d, 0));
+
+    rc = lh_warp_normalize(s.d_images, (int64_t)img_bytes, c.src_h, c.src_w, c.src_w * 3, s.d_affine,
+                           io->flip ? s.d_flip : nullptr, nullptr, c.mean_std, p->d_lut, c.interp, LH_CHAN_RGB,
+                           LH_LAYOUT_CHW, p->d_input, (int)N, c.out_h, c.out_w, p->s_comp);
+    if (rc) goto fail;
+    {
+        lh_heatmap_args a{};
+        a.pred = p->d_pred; a.joints = s.d_joints; a.gauss_table = p->d_table;
+        a.target_out = p->d_target; a.grad = p->d_grad;
+        a.loss_f32 = s.d_loss; a.loss_meter = p->d_sums + 1; a.coords = s.d_coords; a.maxvals = s.d_maxvals; a.ws = p->d_ws;
+        a.N = (int64_t)N; a.J = c.J; a.H = c.H; a.W = c.W; a.joint_stride = 2; a.table_side = p->table_side;
+        a.style = LH_TARGET_HRNET; a.use_target_weight = 0; a.subpixel = c.subpixel;
+        a.stride_x = (float)c.out_w / (float)c.W; a.stride_y = (float)c.out_h / (float)c.H;
+        a.out_scale = a.stride_x;
+        rc = lh_heatmap_fused(&a, p->s_comp);
+        if (rc) goto fail;
+    }
+    rc = lh_pck_epe_batch(s.d_coords, s.d_joints, 2, (int64_t)N, c.J, c.pck_T, LH_PCK_PROPORTION, 0,
+                          p->d_counts, p->d_sums, p->s_comp);
+    if (rc) goto fail;
+    PCHK(cudaMemcpyAsync(s.h_out, s.d_loss, sizeof(float), cudaMemcpyDeviceToHost, p->s_comp));
+    if (io->coords) PCHK(cudaMemcpyAsync(s.h_out + p->off_coords, s.d_coords, N * J * 2 * sizeof(float), cudaMemcpyDeviceToHost, p->s_comp));
+    if (io->maxvals) PCHK(cudaMemcpyAsync(s.h_out + p->off_maxvals, s.d_maxvals, N * J * sizeof(float), cudaMemcpyDeviceToHost, p->s_comp));
+    PCHK(cudaMemcpyAsync(s.h_out + p->off_counts, p->d_counts, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->s_comp));
+    PCHK(cudaMemcpyAsync(s.h_out + p->off_sums, p->d_sums, 4 * sizeof(double), cudaMemcpyDeviceToHost, p->s_comp));
+    PCHK(cudaEventRecord(s.ev_done, p->s_comp));
+    s.io = *io;
+    s.busy = true;
+    p->step++;
+    *slot_out = si;
+    return LH_OK;
+fail:
+    return rc;
+}
+
+// block until slot `si` finished and hand its results to the host pointers given at submit time
+extern "C" int lh_pipeline_wait(lh_pipeline* p, int si) {
+    if (!p) return LH_ENULL;
+    if (si < 0 || si >= kSlots) return LH_EINVAL;
+    Slot& s = p->slot[si];
+    if (!s.busy) return LH_EINVAL;
+    cudaSetDevice(p->cfg.device);
+    cudaError_t e = cudaEventSynchronize(s.ev_done);
+    s.busy = false;
+    if (e != cudaSuccess) return (int)e;
+    const size_t N = p->cfg.batch, J = p->cfg.J;
+    if (s.io.loss) std::memcpy(s.io.loss, s.h_out, sizeof(float));
+    if (s.io.coords) std::memcpy(s.io.coords, s.h_out + p->off_coords, N * J * 2 * sizeof(float));
+    if (s.io.maxvals) std::memcpy(s.io.maxvals, s.h_out + p->off_maxvals, N * J * sizeof(float));
+    if (s.io.counts) std::memcpy(s.io.counts, s.h_out + p->off_counts, 4 * sizeof(unsigned long long));
+    if (s.io.sums) std::memcpy(s.io.sums, s.h_out + p->off_sums, 4 * sizeof(double));
+    return LH_OK;
+}
+
+extern "C" int lh_pipeline_step_host(lh_pipeline* p, const lh_pipeline_io* io) {
+    int si = -1;
+    const int rc = lh_pipeline_submit(p, io, &si);
+    if (rc) return rc;
+    return lh_pipeline_wait(p, si);
+}
+
+// pinned host allocations for callers that want full-rate DMA into the pipeline
+extern "C" void* lh_host_alloc(size_t bytes) {
+    void* q = nullptr;
+    if (cudaMallocHost(&q, bytes) != cudaSuccess) return nullptr;
+    return q;
+}
+extern "C" void lh_host_free(void* q) { if (q) cudaFreeHost(q); }

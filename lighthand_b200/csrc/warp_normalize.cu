@@ -1,0 +1,385 @@
+// K1: batched affine crop / flip / rotate (+ colour gain) + mean/std normalise, uint8 HWC -> float32.
+//
+//   generate_patch_image  src/utils/preprocessing.py:144-162  (cv2.warpAffine INTER_LINEAR, border 0)
+//   colour gain + clip    src/utils/preprocessing.py:81
+//   ToTensor/Normalize    src/tools/dataset.py:147-157
+//   ToTensor/Resize/Norm  src/tools/dataset.py:147-157 (LH_INTERP_TORCH)
+//
+// cv2 parity needs cv2's fixed-point sampling grid: the inverse matrix is
+// formed in double exactly like OpenCV, coordinates are quantised to 1/32 px with round-half-even,
+// and the uint8 result is (sum p*w + 2^14) >> 15 with w = 32*wx*wy  ==  (sum p*wx*wy + 512) >> 10.
+//
+// Layout: one CTA = one 32x32 output tile of one image, 256 threads, 4 consecutive x per thread.
+// The source footprint of the tile (a rotated rectangle) is bounded from the tile corners, its
+// bounding rows are staged into shared memory with 16-byte coalesced loads, and the four taps are
+// fetched from there as aligned 32-bit words + funnel shifts.  The uint8 result indexes a 3x256
+// float table (exact (v/255-mean)/std, optionally per image with the colour gain folded in), so
+// the normalisation costs no divisions.  Output: three 16-byte streaming stores per thread.
+#include "lh_common.cuh"
+
+namespace lh {
+
+constexpr int kTile = 32;
+constexpr int kWThreads = 256;
+constexpr int kStageBytes = 24 * 1024;
+
+struct WarpParams {
+    const uint8_t* src;
+    long long img_stride;
+    int sh, sw, pitch;
+    const double* M;
+    const uint8_t* flip;
+    const double* gain;
+    const float* lut;
+    int lut_per_image;
+    int normalise;
+    float mean[3], stdv[3];
+    int chan_order, layout;
+    float* dst;
+    int N, oh, ow;
+    int vec_store;
+};
+
+__device__ __forceinline__ int sat_i32(double v) {
+    // cv::saturate_cast<int>(double) == cvRound (round-half-even) with saturation
+    if (!(v > -2147483648.0)) return (v != v) ? (int)0x80000000 : (int)0x80000000;
+    if (v >= 2147483647.0) return 0x7fffffff;
+    return __double2int_rn(v);
+}
+
+// OpenCV's in-place inversion of the forward 2x3 matrix (imgwarp.cpp; Appendix A step 1).
+__device__ __forceinline__ void invert_affine(const double* M, double* o) {
+    double m0 = M[0], m1 = M[1], m2 = M[2], m3 = M[3], m4 = M[4], m5 = M[5];
+    double D = __dsub_rn(__dmul_rn(m0, m4), __dmul_rn(m1, m3));
+    D = (D != 0.0) ? __ddiv_rn(1.0, D) : 0.0;
+    const double a11 = __dmul_rn(m4, D), a22 = __dmul_rn(m0, D);
+    m0 = a11; m1 = __dmul_rn(m1, -D); m3 = __dmul_rn(m3, -D); m4 = a22;
+    const double b1 = __dsub_rn(__dmul_rn(-m0, m2), __dmul_rn(m1, m5));
+    const double b2 = __dsub_rn(__dmul_rn(-m3, m2), __dmul_rn(m4, m5));
+    o[0] = m0; o[1] = m1; o[2] = b1; o[3] = m3; o[4] = m4; o[5] = b2;
+}
+
+__device__ __forceinline__ uint32_t lds32(const uint8_t* base, int word) {
+    return reinterpret_cast<const uint32_t*>(base)[word];
+}
+
+// fetch the 6 bytes [off, off+6) of a staged row as two words (bytes 0-3, bytes 4-7)
+__device__ __forceinline__ void load6(const uint8_t* s, int off, uint32_t& lo, uint32_t& hi) {
+    const int w = off >> 2;
+    const uint32_t sh = (off & 3) * 8;
+    const uint32_t a = lds32(s, w), b = lds32(s, w + 1), c = lds32(s, w + 2);
+    lo = __funnelshift_r(a, b, sh);
+    hi = __funnelshift_r(b, c, sh);
+}
+
+__device__ __forceinline__ float finish_f32(float v, int c, double g, const WarpParams& p) {
+    if (p.gain) v = (float)fmin(fmax(__dmul_rn((double)v, g), 0.0), 255.0);
+    if (p.normalise) {
+        v = __fdiv_rn(v, 255.0f);
+        v = __fdiv_rn(__fsub_rn(v, p.mean[c]), p.stdv[c]);
+    }
+    return v;
+}
+
+
+// write one thread's 4 pixels x 3 channels; CHW -> three 16-byte stores, HWC -> three 16-byte stores
+__device__ __forceinline__ void store_tile(const WarpParams& p, float (&out)[3][4], int n, int oy, int ox) {
+    if (p.chan_order == LH_CHAN_BGR) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float t = out[0][k]; out[0][k] = out[2][k]; out[2][k] = t; }
+    }
+    const bool vec = p.vec_store && ox + 3 < p.ow;
+    if (p.layout == LH_LAYOUT_CHW) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float* d = p.dst + (((size_t)n * 3 + c) * p.oh + oy) * p.ow + ox;
+            if (vec) {
+                stg_cs4(d, make_float4(out[c][0], out[c][1], out[c][2], out[c][3]));
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (ox + k < p.ow) d[k] = out[c][k];
+            }
+        }
+    } else {
+        float* d = p.dst + (((size_t)n * p.oh + oy) * p.ow + ox) * 3;
+        if (vec) {
+            stg_cs4(d + 0, make_float4(out[0][0], out[1][0], out[2][0], out[0][1]));
+            stg_cs4(d + 4, make_float4(out[1][1], out[2][1], out[0][2], out[1][2]));
+            stg_cs4(d + 8, make_float4(out[2][2], out[0][3], out[1][3], out[2][3]));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (ox + k < p.ow) {
+                d[3 * k + 0] = out[0][k]; d[3 * k + 1] = out[1][k]; d[3 * k + 2] = out[2][k];
+            }
+        }
+    }
+}
+
+template <bool F32, bool STAGE>
+__global__ void __launch_bounds__(kWThreads) warp_cv2_kernel(const WarpParams p) {
+    __shared__ __align__(16) uint8_t s_stage[STAGE ? (kStageBytes + 32) : 16];
+    __shared__ float s_lut[F32 ? 1 : 768];
+    __shared__ int s_ad[kTile], s_bd[kTile], s_x0[kTile], s_y0[kTile];
+    __shared__ double s_im[6];
+    __shared__ int s_box[6];  // ry0, nrows, byte_start, row_pitch, staged_ok, -
+
+    const int tid = threadIdx.x;
+    const int n = blockIdx.z;
+    const int tx0 = blockIdx.x * kTile, ty0 = blockIdx.y * kTile;
+    const uint8_t* img = p.src + (long long)n * p.img_stride;
+    const bool flip = p.flip ? (p.flip[n] != 0) : false;
+
+    if (tid == 0) invert_affine(p.M + (long long)n * 6, s_im);
+    if (!F32) {
+        const float* lut = p.lut + (p.lut_per_image ? (size_t)n * 768 : 0);
+        for (int i = tid; i < 768; i += kWThreads) s_lut[i] = lut[i];
+    }
+    __syncthreads();
+    if (tid < kTile) {
+        const double x = (double)(tx0 + tid);
+        s_ad[tid] = sat_i32(__dmul_rn(__dmul_rn(s_im[0], x), 1024.0));
+        s_bd[tid] = sat_i32(__dmul_rn(__dmul_rn(s_im[3], x), 1024.0));
+    } else if (tid < 2 * kTile) {
+        const int r = tid - kTile;
+        const double y = (double)(ty0 + r);
+        s_x0[r] = sat_i32(__dmul_rn(__dadd_rn(__dmul_rn(s_im[1], y), s_im[2]), 1024.0)) + 16;
+        s_y0[r] = sat_i32(__dmul_rn(__dadd_rn(__dmul_rn(s_im[4], y), s_im[5]), 1024.0)) + 16;
+    }
+    __syncthreads();
+
+    int ry0 = 0, nrows = 0, bstart = 0, spitch = 0;
+    if (STAGE) {
+        if (tid == 0) {
+            const int cl = min(kTile, p.ow - tx0) - 1, rl = min(kTile, p.oh - ty0) - 1;
+            int xmin = 0x7fffffff, xmax = -0x7fffffff, ymin = 0x7fffffff, ymax = -0x7fffffff;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int r = (k & 1) ? rl : 0, c = (k & 2) ? cl : 0;
+                const int X = (s_x0[r] + s_ad[c]) >> 10, Y = (s_y0[r] + s_bd[c]) >> 10;
+                xmin = min(xmin, X); xmax = max(xmax, X);
+                ymin = min(ymin, Y); ymax = max(ymax, Y);
+            }
+            int lx0 = max(xmin, 0), lx1 = min(xmax + 1, p.sw - 1);
+            int y0 = max(ymin, 0), y1 = min(ymax + 1, p.sh - 1);
+            int ok = 1, nr = 0, bs = 0, sp = 16;
+            if (lx0 <= lx1 && y0 <= y1) {
+                const int pc0 = flip ? p.sw - 1 - lx1 : lx0, pc1 = flip ? p.sw - 1 - lx0 : lx1;
+                bs = (3 * pc0) & ~15;
+                const int be = (3 * (pc1 + 1) + 15) & ~15;
+                sp = be - bs;
+                nr = y1 - y0 + 1;
+                if ((long long)nr * sp > kStageBytes) ok = 0;
+            }
+            s_box[0] = y0; s_box[1] = nr; s_box[2] = bs; s_box[3] = sp; s_box[4] = ok;
+        }
+        __syncthreads();
+        ry0 = s_box[0]; nrows = s_box[1]; bstart = s_box[2]; spitch = s_box[3];
+        if (s_box[4]) {
+            const int vpr = spitch >> 4;
+            const int total = nrows * vpr;
+            for (int v = tid; v < total; v += kWThreads) {
+                const int r = v / vpr, c = v - r * vpr;
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(img + (long long)(ry0 + r) * p.pitch + bstart + c * 16));
+                *reinterpret_cast<uint4*>(s_stage + r * spitch + c * 16) = q;
+            }
+            __syncthreads();
+        }
+    }
+    const bool staged = STAGE && s_box[4];
+
+    const int ty = tid >> 3, txl = (tid & 7) * 4;
+    const int oy = ty0 + ty, ox = tx0 + txl;
+    if (oy >= p.oh || ox >= p.ow) return;
+
+    double g[3] = {1.0, 1.0, 1.0};
+    if (F32 && p.gain) { g[0] = p.gain[n * 3]; g[1] = p.gain[n * 3 + 1]; g[2] = p.gain[n * 3 + 2]; }
+
+    float out[3][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int X = (s_x0[ty] + s_ad[min(txl + k, kTile - 1)]) >> 5;
+        const int Y = (s_y0[ty] + s_bd[min(txl + k, kTile - 1)]) >> 5;
+        const int ix = X >> 5, iy = Y >> 5, ax = X & 31, ay = Y & 31;
+        // tap values: [row 0/1][pixel A (ix) / B (ix+1)] packed as 0x00BBGGRR
+        uint32_t a0 = 0, b0 = 0, a1 = 0, b1 = 0;
+        const bool inside = ix >= 0 && ix + 1 < p.sw && iy >= 0 && iy + 1 < p.sh;
+        if (inside && staged) {
+            const int pc = flip ? p.sw - 2 - ix : ix;
+            const int off = 3 * pc - bstart;
+            uint32_t lo, hi;
+            load6(s_stage + (iy - ry0) * spitch, off, lo, hi);
+            uint32_t f = lo & 0x00ffffffu, s = (lo >> 24) | ((hi & 0xffffu) << 8);
+            a0 = flip ? s : f; b0 = flip ? f : s;
+            load6(s_stage + (iy + 1 - ry0) * spitch, off, lo, hi);
+            f = lo & 0x00ffffffu; s = (lo >> 24) | ((hi & 0xffffu) << 8);
+            a1 = flip ? s : f; b1 = flip ? f : s;
+        } else {
+            // border pixels (some taps outside -> constant 0) and the unstaged fallback
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int xx = ix + (t & 1), yy = iy + (t >> 1);
+                uint32_t v = 0;
+                if (xx >= 0 && xx < p.sw && yy >= 0 && yy < p.sh) {
+                    const int pc = flip ? p.sw - 1 - xx : xx;
+                    if (staged) {
+                        const uint8_t* q = s_stage + (yy - ry0) * spitch + 3 * pc - bstart;
+                        v = q[0] | (q[1] << 8) | (q[2] << 16);
+                    } else {
+                        const uint8_t* q = img + (long long)yy * p.pitch + 3 * pc;
+                        v = __ldg(q) | (__ldg(q + 1) << 8) | (__ldg(q + 2) << 16);
+                    }
+                }
+                if (t == 0) a0 = v; else if (t == 1) b0 = v; else if (t == 2) a1 = v; else b1 = v;
+            }
+        }
+        if (!F32) {
+            const int wx0 = 32 - ax, wy0 = 32 - ay;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int sft = 8 * c;
+                const int h0 = (int)((a0 >> sft) & 0xff) * wx0 + (int)((b0 >> sft) & 0xff) * ax;
+                const int h1 = (int)((a1 >> sft) & 0xff) * wx0 + (int)((b1 >> sft) & 0xff) * ax;
+                const int v = (h0 * wy0 + h1 * ay + 512) >> 10;
+                out[c][k] = s_lut[c * 256 + v];
+            }
+        } else {
+            const float fx = __fmul_rn((float)ax, 0.03125f), fy = __fmul_rn((float)ay, 0.03125f);
+            const float ux = __fsub_rn(1.0f, fx), uy = __fsub_rn(1.0f, fy);
+            const float w00 = __fmul_rn(uy, ux), w01 = __fmul_rn(uy, fx);
+            const float w10 = __fmul_rn(fy, ux), w11 = __fmul_rn(fy, fx);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int sft = 8 * c;
+                float v = __fmul_rn((float)((a0 >> sft) & 0xff), w00);
+                v = __fadd_rn(v, __fmul_rn((float)((b0 >> sft) & 0xff), w01));
+                v = __fadd_rn(v, __fmul_rn((float)((a1 >> sft) & 0xff), w10));
+                v = __fadd_rn(v, __fmul_rn((float)((b1 >> sft) & 0xff), w11));
+                out[c][k] = finish_f32(v, c, g[c], p);
+            }
+        }
+    }
+
+    store_tile(p, out, n, oy, ox);
+}
+
+// LH_INTERP_TORCH: ToTensor -> Resize(bilinear, align_corners=False, no antialias) -> Normalize.
+// float32 in ATen's order: wy0*(wx0*p00 + wx1*p01) + wy1*(wx0*p10 + wx1*p11), p = u8/255.
+__global__ void __launch_bounds__(kWThreads) resize_torch_kernel(const WarpParams p) {
+    __shared__ float s_u[256];
+    const int tid = threadIdx.x;
+    s_u[tid] = __fdiv_rn((float)tid, 255.0f);
+    __syncthreads();
+    const int n = blockIdx.z;
+    const int oy = blockIdx.y * kTile + (tid >> 3);
+    const int ox = blockIdx.x * kTile + (tid & 7) * 4;
+    if (oy >= p.oh || ox >= p.ow) return;
+    const uint8_t* img = p.src + (long long)n * p.img_stride;
+    const bool flip = p.flip ? (p.flip[n] != 0) : false;
+    const float sy = __fdiv_rn((float)p.sh, (float)p.oh), sx = __fdiv_rn((float)p.sw, (float)p.ow);
+    float fy = __fsub_rn(__fmul_rn(sy, __fadd_rn((float)oy, 0.5f)), 0.5f);
+    fy = fy < 0.f ? 0.f : fy;
+    const int y0 = min((int)fy, p.sh - 1), y1 = min(y0 + 1, p.sh - 1);
+    const float ly1 = fminf(fmaxf(__fsub_rn(fy, (float)y0), 0.f), 1.f), ly0 = __fsub_rn(1.0f, ly1);
+    double g[3] = {1.0, 1.0, 1.0};
+    if (p.gain) { g[0] = p.gain[n * 3]; g[1] = p.gain[n * 3 + 1]; g[2] = p.gain[n * 3 + 2]; }
+    float out[3][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float fx = __fsub_rn(__fmul_rn(sx, __fadd_rn((float)(ox + k), 0.5f)), 0.5f);
+        fx = fx < 0.f ? 0.f : fx;
+        int x0 = min((int)fx, p.sw - 1), x1 = min(x0 + 1, p.sw - 1);
+        const float lx1 = fminf(fmaxf(__fsub_rn(fx, (float)x0), 0.f), 1.f), lx0 = __fsub_rn(1.0f, lx1);
+        if (flip) { x0 = p.sw - 1 - x0; x1 = p.sw - 1 - x1; }
+        const uint8_t* r0 = img + (long long)y0 * p.pitch;
+        const uint8_t* r1 = img + (long long)y1 * p.pitch;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float p00 = s_u[__ldg(r0 + 3 * x0 + c)], p01 = s_u[__ldg(r0 + 3 * x1 + c)];
+            const float p10 = s_u[__ldg(r1 + 3 * x0 + c)], p11 = s_u[__ldg(r1 + 3 * x1 + c)];
+            const float top = __fadd_rn(__fmul_rn(lx0, p00), __fmul_rn(lx1, p01));
+            const float bot = __fadd_rn(__fmul_rn(lx0, p10), __fmul_rn(lx1, p11));
+            float v = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+            if (p.gain) v = (float)fmin(fmax(__dmul_rn((double)v, g[c]), 0.0), 1.0);
+            if (p.normalise) v = __fdiv_rn(__fsub_rn(v, p.mean[c]), p.stdv[c]);
+            out[c][k] = v;
+        }
+    }
+    store_tile(p, out, n, oy, ox);
+}
+
+__global__ void norm_lut_kernel(const double* gain, int tables, int normalise, float m0, float m1, float m2,
+                                float s0, float s1, float s2, float* lut) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= tables * 768) return;
+    const int t = i / 768, c = (i % 768) >> 8, v = i & 255;
+    float x = (float)v;
+    if (gain) x = (float)fmin(fmax(__dmul_rn((double)x, gain[t * 3 + c]), 0.0), 255.0);
+    if (normalise) {
+        const float m = c == 0 ? m0 : (c == 1 ? m1 : m2), s = c == 0 ? s0 : (c == 1 ? s1 : s2);
+        x = __fdiv_rn(x, 255.0f);
+        x = __fdiv_rn(__fsub_rn(x, m), s);
+    }
+    lut[i] = x;
+}
+
+}  // namespace lh
+
+using namespace lh;
+
+extern "C" int lh_norm_lut_build(const double* chan_gain, int N, const float* mean_std, float* lut,
+                                 lh_stream_t stream) {
+    if (!lut) return LH_ENULL;
+    const int tables = chan_gain ? N : 1;
+    if (tables < 0) return LH_EINVAL;
+    if (tables == 0) return LH_OK;
+    float ms[6] = {0, 0, 0, 1, 1, 1};
+    if (mean_std) for (int i = 0; i < 6; ++i) ms[i] = mean_std[i];
+    const int total = tables * 768;
+    norm_lut_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        chan_gain, tables, mean_std != nullptr, ms[0], ms[1], ms[2], ms[3], ms[4], ms[5], lut);
+    LH_CHECK_LAUNCH();
+    return LH_OK;
+}
+
+extern "C" int lh_warp_normalize(const uint8_t* src, int64_t src_img_stride, int src_h, int src_w, int src_pitch,
+                                 const double* fwd_affine, const uint8_t* flip, const double* chan_gain,
+                                 const float* mean_std, const float* lut, int interp, int chan_order,
+                                 int out_layout, float* dst, int N, int out_h, int out_w, lh_stream_t stream) {
+    if (!src || !dst) return LH_ENULL;
+    if (N < 0 || src_h <= 0 || src_w <= 0 || out_h <= 0 || out_w <= 0) return LH_EINVAL;
+    if (src_pitch < 3 * src_w || src_img_stride < (int64_t)src_pitch * src_h) return LH_EINVAL;
+    if (src_h > 32766 || src_w > 32766) return LH_EUNSUPPORTED;  // cv2 keeps coordinates in int16
+    if (interp < LH_INTERP_CV2_U8 || interp > LH_INTERP_TORCH) return LH_EINVAL;
+    if (chan_order != LH_CHAN_RGB && chan_order != LH_CHAN_BGR) return LH_EINVAL;
+    if (out_layout != LH_LAYOUT_CHW && out_layout != LH_LAYOUT_HWC) return LH_EINVAL;
+    if (interp != LH_INTERP_TORCH && !fwd_affine) return LH_ENULL;
+    if (interp == LH_INTERP_CV2_U8 && !lut) return LH_ENULL;
+    if (N == 0) return LH_OK;
+    if (N > 65535) return LH_EUNSUPPORTED;  // gridDim.z; callers chunk larger batches
+
+    WarpParams p{};
+    p.src = src; p.img_stride = src_img_stride; p.sh = src_h; p.sw = src_w; p.pitch = src_pitch;
+    p.M = fwd_affine; p.flip = flip; p.gain = chan_gain; p.lut = lut;
+    p.lut_per_image = chan_gain != nullptr;
+    p.normalise = mean_std != nullptr;
+    for (int i = 0; i < 3; ++i) { p.mean[i] = mean_std ? mean_std[i] : 0.f; p.stdv[i] = mean_std ? mean_std[3 + i] : 1.f; }
+    p.chan_order = chan_order; p.layout = out_layout; p.dst = dst; p.N = N; p.oh = out_h; p.ow = out_w;
+    p.vec_store = aligned16(dst) && (out_w % 4 == 0);
+
+    dim3 grid((out_w + kTile - 1) / kTile, (out_h + kTile - 1) / kTile, N), block(kWThreads);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (interp == LH_INTERP_TORCH) {
+        resize_torch_kernel<<<grid, block, 0, st>>>(p);
+    } else {
+        const bool stage = aligned16(src) && (src_pitch % 16 == 0) && (src_img_stride % 16 == 0);
+        if (interp == LH_INTERP_CV2_U8) {
+            if (stage) warp_cv2_kernel<false, true><<<grid, block, 0, st>>>(p);
+            else       warp_cv2_kernel<false, false><<<grid, block, 0, st>>>(p);
+        } else {
+            if (stage) warp_cv2_kernel<true, true><<<grid, block, 0, st>>>(p);
+            else       warp_cv2_kernel<true, false><<<grid, block, 0, st>>>(p);
+        }
+    }
+    LH_CHECK_LAUNCH();
+    return LH_OK;
+}

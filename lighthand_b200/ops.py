@@ -1,0 +1,370 @@
+"""Batched device ops: thin torch-tensor wrappers over the C ABI (one call = one kernel launch,
+asynchronous on torch's current stream).  torch is used for device memory and streams only.
+
+No CPU path exists: every function raises unless its tensors live on a CUDA device and the
+sm_100a library is built.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (LH_CHAN_BGR, LH_CHAN_RGB, LH_INTERP_CV2_F32, LH_INTERP_CV2_U8, LH_INTERP_TORCH,
+                   LH_LAYOUT_CHW, LH_LAYOUT_HWC, LH_PCK_MM, LH_PCK_PROPORTION, LH_TARGET_HOURGLASS,
+                   LH_TARGET_HRNET, LighthandError, check)
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise LighthandError("lighthand_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
+
+
+def _dev(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise LighthandError(f"{name}: expected a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise LighthandError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _mean_std(mean, std):
+    if mean is None:
+        return None
+    arr = (C.c_float * 6)(*[float(np.float32(v)) for v in (*mean, *std)])
+    return arr
+
+
+# ---------------------------------------------------------------------------------------------
+# Gaussian tables, computed on the host exactly as the reference computes them (bit-exact targets)
+# ---------------------------------------------------------------------------------------------
+_table_cache = {}
+
+
+def hrnet_table(sigma: float, device) -> Tuple[torch.Tensor, int]:
+    """float32 numpy exp table of src/tools/dataset.py:189-195 for tmp_size = 3*sigma."""
+    key = ("hrnet", float(sigma), str(device))
+    if key not in _table_cache:
+        tmp = int(sigma * 3)
+        size = 2 * tmp + 1
+        x = np.arange(0, size, 1, np.float32)
+        y = x[:, None]
+        c = size // 2
+        g = np.exp(-((x - c) ** 2 + (y - c) ** 2) / (2 * sigma ** 2)).astype(np.float32)
+        _table_cache[key] = (torch.from_numpy(g).to(device).contiguous(), size)
+    return _table_cache[key]
+
+
+def hourglass_table(output_res: int, device) -> Tuple[torch.Tensor, int]:
+    """float64 table of src/utils/dataset_loader.py:23-32 rounded to float32 (what the paste stores)."""
+    key = ("hg", int(output_res), str(device))
+    if key not in _table_cache:
+        if output_res % 64 != 0:
+            raise LighthandError("GenerateHeatmap: output_res must be a multiple of 64 (integer sigma)")
+        sigma = output_res / 64
+        size = 6 * sigma + 3
+        x = np.arange(0, size, 1, float)
+        y = x[:, None]
+        c = 3 * sigma + 1
+        g = np.exp(-((x - c) ** 2 + (y - c) ** 2) / (2 * sigma ** 2)).astype(np.float32)
+        _table_cache[key] = (torch.from_numpy(g).to(device).contiguous(), int(size))
+    return _table_cache[key]
+
+
+# ---------------------------------------------------------------------------------------------
+# K1
+# ---------------------------------------------------------------------------------------------
+
+def build_norm_lut(mean=IMAGENET_MEAN, std=IMAGENET_STD, chan_gain: Optional[torch.Tensor] = None,
+                   device=None) -> torch.Tensor:
+    """[T,3,256] float32 table: ((clip(v*gain,0,255))/255 - mean)/std; T = N with gain else 1.
+    mean=None gives the identity table (0..255 floats)."""
+    require_cuda()
+    lib = _lib.load()
+    if chan_gain is not None:
+        chan_gain = _dev(chan_gain, torch.float64, "chan_gain")
+        n = chan_gain.shape[0]
+        device = chan_gain.device
+    else:
+        n = 1
+        device = torch.device(device if device is not None else "cuda")
+    lut = torch.empty((n, 3, 256), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        check(lib.lh_norm_lut_build(_ptr(chan_gain), n, _mean_std(mean, std), lut.data_ptr(), _stream()),
+              "lh_norm_lut_build")
+    return lut
+
+
+def warp_normalize(images_u8: torch.Tensor, fwd_affine: Optional[torch.Tensor], out_hw: Sequence[int],
+                   flip: Optional[torch.Tensor] = None, chan_gain: Optional[torch.Tensor] = None,
+                   mean=IMAGENET_MEAN, std=IMAGENET_STD, lut: Optional[torch.Tensor] = None,
+                   interp: int = LH_INTERP_CV2_U8, chan_order: int = LH_CHAN_RGB,
+                   layout: int = LH_LAYOUT_CHW, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K1.  images_u8 [N,Hs,Ws,3] uint8 CUDA; fwd_affine [N,2,3] float64 (src->dst, as cv2.warpAffine
+    takes it); returns float32 [N,3,oh,ow] (CHW) or [N,oh,ow,3] (HWC)."""
+    require_cuda()
+    lib = _lib.load()
+    images_u8 = _dev(images_u8, torch.uint8, "images")
+    if images_u8.dim() != 4 or images_u8.shape[3] != 3:
+        raise LighthandError("images: expected [N,H,W,3] uint8")
+    n, sh, sw, _ = images_u8.shape
+    oh, ow = int(out_hw[0]), int(out_hw[1])
+    if fwd_affine is not None:
+        fwd_affine = _dev(fwd_affine, torch.float64, "fwd_affine")
+        if fwd_affine.numel() != n * 6:
+            raise LighthandError("fwd_affine: expected [N,2,3]")
+    if flip is not None:
+        flip = _dev(flip, torch.uint8, "flip")
+    if chan_gain is not None:
+        chan_gain = _dev(chan_gain, torch.float64, "chan_gain")
+    if interp == LH_INTERP_CV2_U8 and lut is None:
+        lut = build_norm_lut(mean, std, chan_gain, images_u8.device)
+    if lut is not None:
+        lut = _dev(lut, torch.float32, "lut")
+    shape = (n, 3, oh, ow) if layout == LH_LAYOUT_CHW else (n, oh, ow, 3)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=images_u8.device)
+    else:
+        out = _dev(out, torch.float32, "out")
+        if tuple(out.shape) != shape:
+            raise LighthandError("out: wrong shape")
+    with torch.cuda.device(images_u8.device):
+        check(lib.lh_warp_normalize(images_u8.data_ptr(), sh * sw * 3, sh, sw, sw * 3, _ptr(fwd_affine), _ptr(flip),
+                                    _ptr(chan_gain), _mean_std(mean, std), _ptr(lut), interp, chan_order, layout,
+                                    out.data_ptr(), n, oh, ow, _stream()), "lh_warp_normalize")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# K2
+# ---------------------------------------------------------------------------------------------
+
+def gen_targets(joints: torch.Tensor, heatmap_hw=(64, 64), feat_stride=(4.0, 4.0), sigma: float = 2,
+                style: int = LH_TARGET_HRNET, want_weight: bool = True,
+                out: Optional[torch.Tensor] = None):
+    """K2.  joints [N,J,2|3] float32 CUDA (network-input pixels) -> (target [N,J,H,W], weight [N,J,1])."""
+    require_cuda()
+    lib = _lib.load()
+    joints = _dev(joints, torch.float32, "joints")
+    if joints.dim() != 3 or joints.shape[2] < 2:
+        raise LighthandError("joints: expected [N,J,>=2]")
+    n, j, js = joints.shape
+    h, w = int(heatmap_hw[0]), int(heatmap_hw[1])
+    if style == LH_TARGET_HRNET:
+        table, side = hrnet_table(sigma, joints.device)
+    else:
+        if h != w:
+            raise LighthandError("GenerateHeatmap style needs a square map")
+        table, side = hourglass_table(h, joints.device)
+    if out is None:
+        out = torch.empty((n, j, h, w), dtype=torch.float32, device=joints.device)
+    weight = torch.empty((n, j, 1), dtype=torch.float32, device=joints.device) if want_weight else None
+    with torch.cuda.device(joints.device):
+        check(lib.lh_gen_targets(joints.data_ptr(), js, n, j, h, w, float(feat_stride[0]), float(feat_stride[1]),
+                                 style, table.data_ptr(), side, out.data_ptr(), _ptr(weight), _stream()),
+              "lh_gen_targets")
+    return out, weight
+
+
+# ---------------------------------------------------------------------------------------------
+# K3 / K4 / fused
+# ---------------------------------------------------------------------------------------------
+_ws_cache = {}
+
+
+def heatmap_workspace(n: int, j: int, device) -> torch.Tensor:
+    """Zero-initialised workspace (ticket + per-map partials); the kernels leave it clean, so one
+    buffer per (device, stream, size) is reused."""
+    lib = _lib.load()
+    key = (str(device), int(torch.cuda.current_stream(device).cuda_stream), n, j)
+    ws = _ws_cache.get(key)
+    if ws is None:
+        nbytes = lib.lh_heatmap_ws_bytes(n, j)
+        ws = torch.zeros((nbytes + 7) // 8, dtype=torch.int64, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def jmse_loss(pred: torch.Tensor, target: torch.Tensor, weight: Optional[torch.Tensor] = None,
+              want_grad: bool = True):
+    """K3.  Returns (loss float32 0-dim CUDA tensor, grad [N,J,H,W] or None)."""
+    require_cuda()
+    lib = _lib.load()
+    pred = _dev(pred, torch.float32, "pred")
+    target = _dev(target, torch.float32, "target")
+    if pred.dim() != 4 or pred.shape != target.shape:
+        raise LighthandError("pred/target: expected equal [N,J,H,W] shapes")
+    n, j, h, w = pred.shape
+    if weight is not None:
+        weight = _dev(weight, torch.float32, "target_weight").reshape(n, j)
+    loss = torch.empty((), dtype=torch.float32, device=pred.device)
+    grad = torch.empty_like(pred) if want_grad else None
+    with torch.cuda.device(pred.device):
+        ws = heatmap_workspace(n, j, pred.device)
+        check(lib.lh_jmse_loss(pred.data_ptr(), target.data_ptr(), _ptr(weight), n, j, h, w, None,
+                               loss.data_ptr(), _ptr(grad), ws.data_ptr(), _stream()), "lh_jmse_loss")
+    return loss, grad
+
+
+def decode(heat: torch.Tensor, out_scale: float = 1.0, subpixel: bool = False,
+           inv_affine: Optional[torch.Tensor] = None):
+    """K4.  Returns (coords [N,J,2] f32, maxvals [N,J,1] f32, argidx [N,J] i32), all CUDA."""
+    require_cuda()
+    lib = _lib.load()
+    heat = _dev(heat, torch.float32, "heatmaps")
+    if heat.dim() != 4:
+        raise LighthandError("batch_images should be 4-ndim")
+    n, j, h, w = heat.shape
+    if inv_affine is not None:
+        inv_affine = _dev(inv_affine, torch.float64, "inv_affine")
+    coords = torch.empty((n, j, 2), dtype=torch.float32, device=heat.device)
+    maxvals = torch.empty((n, j, 1), dtype=torch.float32, device=heat.device)
+    argidx = torch.empty((n, j), dtype=torch.int32, device=heat.device)
+    with torch.cuda.device(heat.device):
+        check(lib.lh_decode(heat.data_ptr(), n, j, h, w, float(out_scale), int(bool(subpixel)), _ptr(inv_affine),
+                            coords.data_ptr(), maxvals.data_ptr(), argidx.data_ptr(), _stream()), "lh_decode")
+    return coords, maxvals, argidx
+
+
+def heatmap_fused(pred: torch.Tensor, joints: Optional[torch.Tensor] = None, *,
+                  target_in: Optional[torch.Tensor] = None, sigma: float = 2, feat_stride=(4.0, 4.0),
+                  style: int = LH_TARGET_HRNET, want_target: bool = False, want_grad: bool = True,
+                  want_decode: bool = True, out_scale: float = 4.0, subpixel: bool = False,
+                  inv_affine: Optional[torch.Tensor] = None, use_target_weight: bool = False,
+                  loss_meter: Optional[torch.Tensor] = None, buffers: Optional[dict] = None) -> dict:
+    """Fused K2+K3+K4: one read of ``pred`` gives loss, grad, target (optional) and decode.
+    ``buffers`` may carry preallocated outputs (keys: target, grad, loss, coords, maxvals, argidx, weight)
+    so the call is allocation-free (CUDA-graph capturable)."""
+    require_cuda()
+    lib = _lib.load()
+    pred = _dev(pred, torch.float32, "pred")
+    n, j, h, w = pred.shape
+    dev = pred.device
+    b = dict(buffers or {})
+    a = _lib.HeatmapArgs()
+    a.pred = pred.data_ptr()
+    if target_in is not None:
+        target_in = _dev(target_in, torch.float32, "target")
+        a.target_in = target_in.data_ptr()
+    else:
+        if joints is None:
+            raise LighthandError("heatmap_fused: joints or target_in required")
+        joints = _dev(joints, torch.float32, "joints")
+        a.joints = joints.data_ptr()
+        a.joint_stride = joints.shape[2]
+        if style == LH_TARGET_HRNET:
+            table, side = hrnet_table(sigma, dev)
+        else:
+            table, side = hourglass_table(h, dev)
+        a.gauss_table = table.data_ptr()
+        a.table_side = side
+        if want_target:
+            b.setdefault("target", torch.empty_like(pred))
+            a.target_out = b["target"].data_ptr()
+        b.setdefault("weight", torch.empty((n, j, 1), dtype=torch.float32, device=dev))
+        a.target_weight_out = b["weight"].data_ptr()
+    if want_grad:
+        b.setdefault("grad", torch.empty_like(pred))
+        a.grad = b["grad"].data_ptr()
+    b.setdefault("loss", torch.empty((), dtype=torch.float32, device=dev))
+    a.loss_f32 = b["loss"].data_ptr()
+    if loss_meter is not None:
+        a.loss_meter = _dev(loss_meter, torch.float64, "loss_meter").data_ptr()
+    if want_decode:
+        b.setdefault("coords", torch.empty((n, j, 2), dtype=torch.float32, device=dev))
+        b.setdefault("maxvals", torch.empty((n, j, 1), dtype=torch.float32, device=dev))
+        b.setdefault("argidx", torch.empty((n, j), dtype=torch.int32, device=dev))
+        a.coords = b["coords"].data_ptr()
+        a.maxvals = b["maxvals"].data_ptr()
+        a.argidx = b["argidx"].data_ptr()
+    if inv_affine is not None:
+        a.inv_affine = _dev(inv_affine, torch.float64, "inv_affine").data_ptr()
+    a.N, a.J, a.H, a.W = n, j, h, w
+    a.style = style
+    a.use_target_weight = int(bool(use_target_weight))
+    a.subpixel = int(bool(subpixel))
+    a.stride_x, a.stride_y = float(feat_stride[0]), float(feat_stride[1])
+    a.out_scale = float(out_scale)
+    with torch.cuda.device(dev):
+        ws = b.get("ws")
+        if ws is None:
+            ws = heatmap_workspace(n, j, dev)
+        a.ws = ws.data_ptr()
+        check(lib.lh_heatmap_fused(C.byref(a), _stream()), "lh_heatmap_fused")
+    return b
+
+
+# ---------------------------------------------------------------------------------------------
+# K5
+# ---------------------------------------------------------------------------------------------
+
+def new_metric_state(device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(counts int64[4] = n_wrong, n_total, epe_count, n_images ; sums float64[4] = epe_sum, loss*n, n, -)."""
+    return (torch.zeros(4, dtype=torch.int64, device=device), torch.zeros(4, dtype=torch.float64, device=device))
+
+
+def pck_epe_batch(pred_xy: torch.Tensor, gt: torch.Tensor, T: float, threshold: str, visible: bool,
+                  counts: torch.Tensor, sums: torch.Tensor) -> None:
+    """K5 in-loop metrics, accumulating into (counts, sums)."""
+    require_cuda()
+    lib = _lib.load()
+    pred_xy = _dev(pred_xy, torch.float32, "pred_2d")
+    gt = _dev(gt, torch.float32, "gt_2d")
+    n, j, gs = gt.shape
+    if pred_xy.shape[0] != n or pred_xy.shape[1] != j or pred_xy.shape[2] != 2:
+        raise LighthandError("pred_2d: expected [N,J,2] matching gt")
+    if threshold == "proportion":
+        mode, thr = LH_PCK_PROPORTION, float(np.float32(T))
+    elif threshold == "mm":
+        mode, thr = LH_PCK_MM, float(np.float32(T * 3.78))
+    else:
+        raise AssertionError("Please check variable threshold is right")
+    counts = _dev(counts, torch.int64, "counts")
+    sums = _dev(sums, torch.float64, "sums")
+    with torch.cuda.device(gt.device):
+        check(lib.lh_pck_epe_batch(pred_xy.data_ptr(), gt.data_ptr(), gs, n, j, thr, mode, int(bool(visible)),
+                                   counts.data_ptr(), sums.data_ptr(), _stream()), "lh_pck_epe_batch")
+
+
+def pck_curve_accum(pred_xy: torch.Tensor, gt: torch.Tensor, thr_sorted: torch.Tensor, method: str,
+                    use_vis: bool, hist: torch.Tensor, n_valid: torch.Tensor, n_all: torch.Tensor,
+                    sum_d: torch.Tensor, bbox: Optional[torch.Tensor] = None,
+                    category: Optional[torch.Tensor] = None) -> None:
+    """K5 curve histograms (pred_eval / pred_test counting core), accumulating."""
+    require_cuda()
+    lib = _lib.load()
+    pred_xy = _dev(pred_xy, torch.float32, "pred")
+    gt = _dev(gt, torch.float32, "gt")
+    thr_sorted = _dev(thr_sorted, torch.float64, "thresholds")
+    n, j, gs = gt.shape
+    n_cat, kp1 = hist.shape
+    if kp1 != thr_sorted.numel() + 1:
+        raise LighthandError("hist: expected [n_cat, K+1]")
+    if bbox is not None:
+        bbox = _dev(bbox, torch.float32, "bbox")
+    if category is not None:
+        category = _dev(category, torch.int32, "category")
+    if method not in ("mm", "pckb"):
+        raise AssertionError("this method is the wrong")
+    with torch.cuda.device(gt.device):
+        check(lib.lh_pck_curve_accum(pred_xy.data_ptr(), gt.data_ptr(), gs, _ptr(bbox), _ptr(category), n_cat, n, j,
+                                     thr_sorted.data_ptr(), thr_sorted.numel(), 1 if method == "pckb" else 0,
+                                     int(bool(use_vis)), _dev(hist, torch.int64, "hist").data_ptr(),
+                                     _dev(n_valid, torch.int64, "n_valid").data_ptr(),
+                                     _dev(n_all, torch.int64, "n_all").data_ptr(),
+                                     _dev(sum_d, torch.float64, "sum_d").data_ptr(), _stream()),
+              "lh_pck_curve_accum")

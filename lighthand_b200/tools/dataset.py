@@ -1,0 +1,61 @@
+"""Target generation and batch collation with the reference's call surface (src/tools/dataset.py).
+
+``generate_target`` replaces CustomDataset.generate_target (src/tools/dataset.py:165-212 and its three
+verbatim copies); ``GpuCollate`` replaces ``CustomDataset.__getitem__`` + default collate
+(src/tools/dataset.py:125-163): DataLoader workers ship uint8 HWC images + keypoints, the
+ToTensor -> Resize -> Normalize and the Gaussian targets run batched on the device.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..utils.loss import _to_cuda
+
+
+def generate_target(joints, num_joints=21, heatmap_size=(64, 64), feat_stride=(4, 4), sigma=2,
+                    return_weight=False):
+    """One sample [J,2] (or a batch [N,J,2]) of input-pixel joints -> float32 target [J,H,W].
+    Defaults are the reference's hard-coded geometry.  CPU input -> CPU tensor (like the
+    reference's ``torch.tensor(target)``), CUDA input -> CUDA tensor."""
+    on_dev = isinstance(joints, torch.Tensor) and joints.is_cuda
+    t = _to_cuda(joints)
+    single = t.dim() == 2
+    if single:
+        t = t[None]
+    if t.shape[1] != num_joints:
+        raise ops.LighthandError("generate_target: wrong number of joints")
+    target, weight = ops.gen_targets(t, heatmap_size, (float(feat_stride[0]), float(feat_stride[1])), sigma,
+                                     style=ops.LH_TARGET_HRNET, want_weight=True)
+    if single:
+        target, weight = target[0], weight[0]
+    if not on_dev:
+        target, weight = target.cpu(), weight.cpu()
+    return (target, weight) if return_weight else target
+
+
+class GpuCollate:
+    """collate_fn for a DataLoader whose dataset yields ``(image_u8_hwc, joint_2d)``:
+    returns ``(images f32[N,3,S,S], joint_2d f32[N,J,2], heatmaps f32[N,J,H,W])`` on ``device`` --
+    the triple the reference's loops consume (src/utils/method.py:160).  Keypoints are scaled by
+    S / S_src (src/tools/dataset.py:132)."""
+
+    def __init__(self, image_size=256, heatmap_size=64, sigma=2, device="cuda",
+                 mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD):
+        self.image_size, self.heatmap_size, self.sigma = image_size, heatmap_size, sigma
+        self.device, self.mean, self.std = torch.device(device), mean, std
+
+    def __call__(self, samples):
+        imgs = np.stack([np.asarray(s[0], dtype=np.uint8) for s in samples])
+        joints = torch.stack([torch.as_tensor(s[1], dtype=torch.float32)[:, :2] for s in samples])
+        src = imgs.shape[1]
+        joints = joints * (self.image_size / src)
+        d_imgs = torch.from_numpy(imgs).to(self.device, non_blocking=True)
+        d_joints = joints.to(self.device, non_blocking=True)
+        images = ops.warp_normalize(d_imgs, None, (self.image_size, self.image_size), mean=self.mean,
+                                    std=self.std, interp=ops.LH_INTERP_TORCH)
+        stride = self.image_size / self.heatmap_size
+        heat, _ = ops.gen_targets(d_joints, (self.heatmap_size, self.heatmap_size), (stride, stride),
+                                  self.sigma, want_weight=False)
+        return images, d_joints, heat
