@@ -1,0 +1,63 @@
+"""The C-ABI library loads and exports exactly what include/lighthand_b200.h declares.  No compute."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from lighthand_b200 import _lib
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "lighthand_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lh_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    syms = _declared_symbols()
+    assert len(syms) >= 20
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in the header but not exported"
+    assert sorted(_lib.PROTOTYPES) == syms, "ctypes prototypes out of sync with the header"
+
+
+def test_version_and_error_text():
+    lib = _lib.load()
+    assert lib.lh_abi_version() == 1
+    assert b"NULL" in lib.lh_strerror(-2)
+    assert lib.lh_strerror(-1).startswith(b"lighthand_b200")
+    assert lib.lh_heatmap_ws_bytes(256, 21) == 16 + 8 * 256 * 21
+
+
+def test_argument_validation_needs_no_device():
+    """Argument errors are reported before any CUDA call (negative codes)."""
+    lib = _lib.load()
+    assert lib.lh_gen_targets(None, 2, 1, 21, 64, 64, 4.0, 4.0, 0, None, 13, None, None, None) == -2
+    assert lib.lh_decode(None, 1, 21, 64, 64, 4.0, 0, None, None, None, None, None) == -2
+    assert lib.lh_jmse_loss(None, None, None, 1, 21, 64, 64, None, None, None, None, None) == -2
+    assert lib.lh_pck_epe_batch(None, None, 2, 1, 21, 0.2, 0, 0, None, None, None) == -2
+    assert lib.lh_warp_normalize(None, 0, 1, 1, 3, None, None, None, None, None, 0, 0, 0, None, 1, 1, 1, None) == -2
+
+
+def test_struct_layout_matches_header():
+    # offsets the C side relies on: pointers first, then N (int64), then int32s / floats
+    assert ctypes.sizeof(_lib.HeatmapArgs) == 15 * 8 + 8 + 8 * 4 + 3 * 4 + 4   # padded to 8
+    assert _lib.HeatmapArgs.N.offset == 120
+    assert ctypes.sizeof(_lib.PipelineCfg) == 13 * 4 + 2 * 4 + 6 * 4
+    assert ctypes.sizeof(_lib.PipelineIO) == 10 * 8
+
+
+def test_ops_refuse_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from lighthand_b200 import ops
+    from lighthand_b200.utils.loss import get_max_preds
+    import numpy as np
+    with pytest.raises(ops.LighthandError):
+        ops.decode(torch.zeros(1, 21, 64, 64))
+    with pytest.raises(ops.LighthandError):
+        get_max_preds(np.zeros((1, 21, 64, 64), np.float32))

@@ -1,0 +1,106 @@
+"""K1 parity: cv2.warpAffine's fixed-point grid (uint8 and float32 weight paths), flip, colour gain,
+normalisation, layouts; torch-style bilinear resize."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import restate as R
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from lighthand_b200 import ops as _ops
+    _ops.require_cuda()
+    return _ops
+
+
+def cu(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def test_patch_golden_u8_and_f32_paths_exact(ops):
+    g = golden("warp.npz")
+    oh, ow = (int(v) for v in g["out_hw"])
+    imgs, M, flip = cu(g["imgs"]), cu(g["trans"].astype(np.float64)), cu(g["flip"].astype(np.uint8))
+    for interp, want in ((ops.LH_INTERP_CV2_U8, g["patch_u8src"]), (ops.LH_INTERP_CV2_F32, g["patch_f32src"])):
+        out = ops.warp_normalize(imgs, M, (oh, ow), flip=flip, mean=None, std=None, interp=interp,
+                                 layout=ops.LH_LAYOUT_HWC)
+        got = out.cpu().numpy()
+        assert np.abs(got - want).max() <= (0.0 if interp == ops.LH_INTERP_CV2_U8 else 1e-4), interp
+        chw = ops.warp_normalize(imgs, M, (oh, ow), flip=flip, mean=None, std=None, interp=interp)
+        assert torch.equal(chw, out.permute(0, 3, 1, 2).contiguous())
+
+
+@pytest.mark.parametrize("src_hw,out_hw", [((256, 256), (256, 256)), ((224, 224), (224, 224)), ((97, 131), (64, 80)), ((300, 200), (96, 100))])
+def test_warp_normalize_random_augmentations_vs_cv2(ops, src_hw, out_hw):
+    """Whole K1 (warp + /255 + mean/std, CHW) against cv2 + torchvision semantics: identical uint8 pixel
+    => identical float (LUT holds torch's float32 result), so the bar 'within 1 LSB' is met with 0."""
+    rng = np.random.default_rng(src_hw[0] + out_hw[1])
+    n = 6
+    imgs = rng.integers(0, 256, (n, *src_hw, 3), dtype=np.uint8)
+    Ms, flips, wants = [], [], []
+    for i in range(n):
+        side = 0.8 * min(src_hw)
+        bbox = [(src_hw[1] - side) / 2 + rng.uniform(-8, 8), (src_hw[0] - side) / 2 + rng.uniform(-8, 8), side, side]
+        scale = float(np.clip(rng.standard_normal(), -1, 1) * 0.25 + 1)
+        rot = float(np.clip(rng.standard_normal(), -2, 2) * 45) if rng.uniform() <= 0.6 else 0.0
+        flip = bool(rng.uniform() <= 0.5)
+        chw, trans, _ = R.warp_normalize_sample(imgs[i], bbox, flip, scale, rot, out_hw)
+        Ms.append(trans.astype(np.float64)); flips.append(flip); wants.append(chw)
+    out = ops.warp_normalize(cu(imgs), cu(np.stack(Ms)), out_hw, flip=cu(np.array(flips, np.uint8)))
+    got, want = out.cpu().numpy(), np.stack(wants)
+    lsb = (1 / 255) / min(R.IMAGENET_STD)
+    assert np.abs(got - want).max() <= 1e-6, np.abs(got - want).max() / lsb
+
+
+def test_warp_unaligned_source_uses_unstaged_path(ops):
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (1, 50, 37, 3), dtype=np.uint8)       # pitch 111: not 16-byte aligned
+    M = R.gen_trans_from_patch_cv(18, 25, 30, 30, 32, 32, 1.0, 20.0).astype(np.float64)[None]
+    out = ops.warp_normalize(cu(img), cu(M), (32, 32), mean=None, std=None, layout=ops.LH_LAYOUT_HWC)
+    want = R.warp_affine_model(img[0], M[0], 32, 32).astype(np.float32)
+    assert np.array_equal(out[0].cpu().numpy(), want)
+
+
+def test_colour_gain_clip_matches_reference_semantics(ops):
+    rng = np.random.default_rng(6)
+    imgs = rng.integers(0, 256, (3, 64, 64, 3), dtype=np.uint8)
+    gain = rng.uniform(0.8, 1.2, (3, 3))
+    Ms = np.stack([R.gen_trans_from_patch_cv(32, 32, 50, 50, 48, 48, 1.0, 15.0 * i) for i in range(3)]).astype(np.float64)
+    out = ops.warp_normalize(cu(imgs), cu(Ms), (48, 48), chan_gain=cu(gain))
+    for i in range(3):
+        patch = R.warp_affine_model(imgs[i], Ms[i], 48, 48).astype(np.float32)
+        want = R.to_tensor_normalize(R.colour_scale_clip(patch, gain[i]).astype(np.float32))
+        np.testing.assert_allclose(out[i].cpu().numpy(), want, rtol=0, atol=1e-6)
+
+
+def test_bgr_channel_order(ops):
+    rng = np.random.default_rng(8)
+    imgs = cu(rng.integers(0, 256, (2, 40, 40, 3), dtype=np.uint8))
+    M = cu(np.stack([np.array([[1.0, 0, 0], [0, 1.0, 0]])] * 2))
+    a = ops.warp_normalize(imgs, M, (40, 40), mean=None, std=None)
+    b = ops.warp_normalize(imgs, M, (40, 40), mean=None, std=None, chan_order=ops.LH_CHAN_BGR)
+    assert torch.equal(a[:, [2, 1, 0]], b)
+    assert torch.equal(a, imgs.permute(0, 3, 1, 2).float())          # identity warp reproduces the source
+
+
+def test_resize_mode_golden(ops):
+    g = golden("resize.npz")
+    out = ops.warp_normalize(cu(g["imgs"]), None, (64, 64), interp=ops.LH_INTERP_TORCH)
+    np.testing.assert_allclose(out.cpu().numpy(), g["out"], rtol=1e-5, atol=1e-5)
+    out = ops.warp_normalize(cu(g["imgs"]), None, (80, 72), interp=ops.LH_INTERP_TORCH)
+    np.testing.assert_allclose(out.cpu().numpy(), g["out_80x72"], rtol=1e-5, atol=1e-5)
+
+
+def test_resize_224_to_256_vs_oracle(ops):
+    rng = np.random.default_rng(9)
+    imgs = rng.integers(0, 256, (2, 224, 224, 3), dtype=np.uint8)
+    out = ops.warp_normalize(cu(imgs), None, (256, 256), interp=ops.LH_INTERP_TORCH).cpu().numpy()
+    for i in range(2):
+        np.testing.assert_allclose(out[i], R.resize_normalize_sample(imgs[i], (256, 256)), rtol=1e-5, atol=1e-5)
