@@ -142,6 +142,8 @@ def warp_normalize(images_u8: torch.Tensor, fwd_affine: Optional[torch.Tensor], 
         out = _dev(out, torch.float32, "out")
         if tuple(out.shape) != shape:
             raise LighthandError("out: wrong shape")
+    if n == 0:
+        return out
     with torch.cuda.device(images_u8.device):
         check(lib.lh_warp_normalize(images_u8.data_ptr(), sh * sw * 3, sh, sw, sw * 3, _ptr(fwd_affine), _ptr(flip),
                                     _ptr(chan_gain), _mean_std(mean, std), _ptr(lut), interp, chan_order, layout,
@@ -173,6 +175,8 @@ def gen_targets(joints: torch.Tensor, heatmap_hw=(64, 64), feat_stride=(4.0, 4.0
     if out is None:
         out = torch.empty((n, j, h, w), dtype=torch.float32, device=joints.device)
     weight = torch.empty((n, j, 1), dtype=torch.float32, device=joints.device) if want_weight else None
+    if n == 0:
+        return out, weight
     with torch.cuda.device(joints.device):
         check(lib.lh_gen_targets(joints.data_ptr(), js, n, j, h, w, float(feat_stride[0]), float(feat_stride[1]),
                                  style, table.data_ptr(), side, out.data_ptr(), _ptr(weight), _stream()),
@@ -234,6 +238,8 @@ def decode(heat: torch.Tensor, out_scale: float = 1.0, subpixel: bool = False,
     coords = torch.empty((n, j, 2), dtype=torch.float32, device=heat.device)
     maxvals = torch.empty((n, j, 1), dtype=torch.float32, device=heat.device)
     argidx = torch.empty((n, j), dtype=torch.int32, device=heat.device)
+    if n == 0:
+        return coords, maxvals, argidx
     with torch.cuda.device(heat.device):
         check(lib.lh_decode(heat.data_ptr(), n, j, h, w, float(out_scale), int(bool(subpixel)), _ptr(inv_affine),
                             coords.data_ptr(), maxvals.data_ptr(), argidx.data_ptr(), _stream()), "lh_decode")
