@@ -107,6 +107,12 @@ class HeatmapPipeline:
         out.pop("ws")
         return out
 
+    def prepare(self, images_u8, fwd_affine, joints, pred, flip=None, inv_affine=None) -> "PreparedStep":
+        """Validate and marshal the three C-ABI calls ONCE for a fixed set of device buffers; the returned
+        object's ``launch()`` then costs three raw ctypes calls (no per-step Python argument work), which
+        keeps the host ahead of a ~150 us device step without needing a CUDA graph."""
+        return PreparedStep(self, images_u8, fwd_affine, joints, pred, flip, inv_affine)
+
     def reset_metrics(self):
         self.meter.reset()
 
@@ -126,6 +132,69 @@ class HeatmapPipeline:
         fused = 4 * self.J * hw * (1 + (1 if self.train else 0) + (1 if self.materialize_target else 0)) + 8 * self.J + 16 * self.J
         k5 = 16 * self.J
         return {"warp_normalize": k1, "heatmap_fused": fused, "pck_epe": k5, "step": k1 + fused + k5}
+
+
+class PreparedStep:
+    """Pre-marshalled K1 -> fused -> K5 launch sequence bound to fixed device buffers."""
+
+    def __init__(self, pipe: HeatmapPipeline, images_u8, fwd_affine, joints, pred, flip, inv_affine):
+        lib = _lib.load()
+        p = pipe
+        images_u8 = ops._dev(images_u8, torch.uint8, "images")
+        joints = ops._dev(joints, torch.float32, "joints")
+        pred = ops._dev(pred, torch.float32, "pred")
+        n, sh, sw, _ = images_u8.shape
+        if n != p.N or tuple(pred.shape) != (p.N, p.J, *p.hm_hw) or (sh, sw) != tuple(p.src_hw):
+            raise LighthandError("prepare: tensor shapes differ from the pipeline configuration")
+        if fwd_affine is not None:
+            fwd_affine = ops._dev(fwd_affine, torch.float64, "fwd_affine")
+        elif p.interp != ops.LH_INTERP_TORCH:
+            raise LighthandError("prepare: fwd_affine required for the cv2 warp modes")
+        if flip is not None:
+            flip = ops._dev(flip, torch.uint8, "flip")
+        if inv_affine is not None:
+            inv_affine = ops._dev(inv_affine, torch.float64, "inv_affine")
+        self._keep = (images_u8, fwd_affine, joints, pred, flip, inv_affine, p)
+        self._ms = ops._mean_std(p.mean, p.std)
+        ptr = ops._ptr
+        self._k1 = (images_u8.data_ptr(), sh * sw * 3, sh, sw, sw * 3, ptr(fwd_affine), ptr(flip), None, self._ms,
+                    ptr(p.lut), p.interp, ops.LH_CHAN_RGB, ops.LH_LAYOUT_CHW, p.input.data_ptr(), n, p.out_hw[0], p.out_hw[1])
+        a = _lib.HeatmapArgs()
+        b = p.buffers
+        table, side = ops.hrnet_table(p.sigma, p.device)
+        a.pred, a.joints, a.gauss_table, a.table_side = pred.data_ptr(), joints.data_ptr(), table.data_ptr(), side
+        a.joint_stride = joints.shape[2]
+        a.target_out = b["target"].data_ptr() if p.materialize_target else None
+        a.target_weight_out = b["weight"].data_ptr()
+        a.grad = b["grad"].data_ptr() if p.train else None
+        a.loss_f32, a.loss_meter = b["loss"].data_ptr(), p.meter.loss_meter.data_ptr()
+        a.coords, a.maxvals, a.argidx = b["coords"].data_ptr(), b["maxvals"].data_ptr(), b["argidx"].data_ptr()
+        a.inv_affine = ptr(inv_affine) if p.map_back else None
+        a.ws = b["ws"].data_ptr()
+        a.N, a.J, a.H, a.W = p.N, p.J, p.hm_hw[0], p.hm_hw[1]
+        a.style, a.use_target_weight, a.subpixel = ops.LH_TARGET_HRNET, 0, int(bool(p.subpixel))
+        a.stride_x, a.stride_y, a.out_scale = float(p.stride[0]), float(p.stride[1]), float(p.stride[0])
+        self._args = a
+        self._k5 = (b["coords"].data_ptr(), joints.data_ptr(), joints.shape[2], p.N, p.J, float(np.float32(p.pck_T)),
+                    ops.LH_PCK_PROPORTION, 0, p.meter.counts.data_ptr(), p.meter.sums.data_ptr())
+        self._f1, self._f2, self._f3 = lib.lh_warp_normalize, lib.lh_heatmap_fused, lib.lh_pck_epe_batch
+        self._aref = C.byref(a)
+
+    def launch(self, stream: Optional[int] = None, events=None) -> None:
+        """Enqueue the step on ``stream`` (raw cudaStream_t; default: torch's current stream).  ``events``
+        = (e0, e1, e2) torch events recorded before K1, after K1 and after the fused kernel."""
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        if events is not None:
+            events[0].record()
+        rc = self._f1(*self._k1, st)
+        if events is not None:
+            events[1].record()
+        rc = rc or self._f2(self._aref, st)
+        if events is not None:
+            events[2].record()
+        rc = rc or self._f3(*self._k5, st)
+        if rc:
+            check(rc, "prepared step")
 
 
 class HostPipeline:
