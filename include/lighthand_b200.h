@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define LH_ABI_VERSION 1
+#define LH_ABI_VERSION 2
 
 #define LH_OK            0
 #define LH_EINVAL       (-1)  /* bad size / enum value */
@@ -115,9 +115,14 @@ int lh_decode(const float* heat, int64_t N, int J, int H, int W, float out_scale
               float* coords, float* maxvals, int32_t* argidx, lh_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
- * K2+K3+K4 fused post-backbone pass: pred is read ONCE; target is generated on the fly from the
- * joints (and written if `target` != NULL), loss/grad and decode come out of the same pass.
+ * K2+K3+K4(+K5) fused post-backbone pass: pred is read ONCE; target is generated on the fly from the
+ * joints (and written if `target_out` != NULL), loss/grad and decode come out of the same pass.  With
+ * metric_counts / metric_sums set, PCK_2d_loss + EPE_train of the decoded joints against `joints`
+ * (src/utils/loss.py:50-67,116-148; all joints, no visibility) are folded into the accumulators of
+ * lh_pck_epe_batch by the last CTA of the same launch.
  * ------------------------------------------------------------------------------------------ */
+#define LH_PCK_PROPORTION 0
+#define LH_PCK_MM         1
 typedef struct lh_heatmap_args {
     const float* pred;          /* dev [N,J,H,W]                                           */
     const float* joints;        /* dev [N,J,joint_stride]  (input-image pixel coordinates) */
@@ -134,6 +139,8 @@ typedef struct lh_heatmap_args {
     float* maxvals;             /* dev [N,J] or NULL                                       */
     int32_t* argidx;            /* dev [N,J] or NULL                                       */
     void* ws;                   /* dev workspace, lh_heatmap_ws_bytes(N,J)                 */
+    unsigned long long* metric_counts; /* dev u64[4] or NULL, see lh_pck_epe_batch          */
+    double* metric_sums;        /* dev f64[4] or NULL                                      */
     int64_t N;
     int32_t J, H, W;
     int32_t joint_stride;
@@ -143,6 +150,8 @@ typedef struct lh_heatmap_args {
     int32_t subpixel;
     float stride_x, stride_y;
     float out_scale;
+    float pck_thr;              /* threshold as float32: T ('proportion') or T*3.78 ('mm') */
+    int32_t pck_mode;           /* LH_PCK_*                                                */
 } lh_heatmap_args;
 int lh_heatmap_fused(const lh_heatmap_args* args, lh_stream_t stream);
 
@@ -157,8 +166,6 @@ int lh_heatmap_fused(const lh_heatmap_args* args, lh_stream_t stream);
  * thr_f32: the threshold already rounded the way torch does it: (float)T for 'proportion',
  * (float)(T*3.78) for 'mm'.
  * ------------------------------------------------------------------------------------------ */
-#define LH_PCK_PROPORTION 0
-#define LH_PCK_MM         1
 int lh_pck_epe_batch(const float* pred_xy /*dev [N,J,2]*/, const float* gt /*dev [N,J,gt_stride]*/, int gt_stride,
                      int64_t N, int J, float thr_f32, int mode, int visible,
                      unsigned long long* counts, double* sums, lh_stream_t stream);
@@ -180,8 +187,8 @@ int lh_pck_curve_accum(const float* pred_xy, const float* gt, int gt_stride,
 
 /* ------------------------------------------------------------------------------------------
  * Host-buffer pipeline context (what a non-torch host binds; also the e2e benchmark path).
- * Owns device buffers, pinned staging, two streams and a CUDA graph of
- *   H2D -> K1 -> fused(K2,K3,K4) -> K5 -> D2H.
+ * Owns device buffers, pinned staging and two streams; one step is
+ *   H2D -> K1 -> fused(K2,K3,K4,K5) -> D2H   (two kernel launches).
  * ------------------------------------------------------------------------------------------ */
 typedef struct lh_pipeline_cfg {
     int32_t device;
@@ -193,6 +200,7 @@ typedef struct lh_pipeline_cfg {
     int32_t train;              /* 1: write grad */
     int32_t materialize_target; /* 1: write the target heat-maps (what the reference's dataset returns) */
     int32_t subpixel;
+    int32_t exact_norm;         /* 1: table normalisation (bit-identical to torch), 0: one FMA (<= 2 ulp) */
     float sigma;
     float pck_T;                /* in-loop PCK threshold, 'proportion' (src/utils/method.py:243) */
     float mean_std[6];

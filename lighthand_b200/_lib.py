@@ -33,9 +33,11 @@ class HeatmapArgs(C.Structure):
         ("pred", c_p), ("joints", c_p), ("gauss_table", c_p), ("target_in", c_p), ("inv_affine", c_p),
         ("target_out", c_p), ("target_weight_out", c_p), ("grad", c_p), ("loss_f64", c_p),
         ("loss_meter", c_p), ("loss_f32", c_p), ("coords", c_p), ("maxvals", c_p), ("argidx", c_p), ("ws", c_p),
+        ("metric_counts", c_p), ("metric_sums", c_p),
         ("N", c_i64), ("J", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("joint_stride", C.c_int32),
         ("table_side", C.c_int32), ("style", C.c_int32), ("use_target_weight", C.c_int32),
-        ("subpixel", C.c_int32), ("stride_x", c_f), ("stride_y", c_f), ("out_scale", c_f),
+        ("subpixel", C.c_int32), ("stride_x", c_f), ("stride_y", c_f), ("out_scale", c_f), ("pck_thr", c_f),
+        ("pck_mode", C.c_int32),
     ]
 
 
@@ -44,7 +46,7 @@ class PipelineCfg(C.Structure):
         ("device", C.c_int32), ("batch", C.c_int32), ("src_h", C.c_int32), ("src_w", C.c_int32),
         ("out_h", C.c_int32), ("out_w", C.c_int32), ("J", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
         ("interp", C.c_int32), ("train", C.c_int32), ("materialize_target", C.c_int32),
-        ("subpixel", C.c_int32), ("sigma", c_f), ("pck_T", c_f), ("mean_std", c_f * 6),
+        ("subpixel", C.c_int32), ("exact_norm", C.c_int32), ("sigma", c_f), ("pck_T", c_f), ("mean_std", c_f * 6),
     ]
 
 
@@ -103,7 +105,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so is stale
         fn.restype = res
         fn.argtypes = args
-    if lib.lh_abi_version() != 1:
+    if lib.lh_abi_version() != 2:
         raise LighthandError("liblighthand_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -1,14 +1,22 @@
-// K2 / K3 / K4 and their fusion: one streaming pass over [N,J,H,W] heat-maps.
+// K2 / K3 / K4 (+ K5) and their fusion: one streaming pass over [N,J,H,W] heat-maps.
 //
 //   gen_targets   (src/tools/dataset.py:165-212, src/utils/dataset_loader.py:22-53)
 //   JointsMSELoss (src/utils/loss.py:306-325) forward + backward
 //   get_max_preds (src/utils/loss.py:327-355) [+ quarter-pixel shift, inverse affine]
+//   PCK_2d_loss / EPE_train (src/utils/loss.py:50-67,116-148) on the decoded joints (optional, fused tail)
 //
-// One CTA of 256 threads owns one (n,j) map: H*W floats are streamed with 16-byte loads/stores,
-// 4 independent vectors in flight per thread; the target value is recomputed from the joint
-// (a <=19x19 table in shared memory) instead of being re-read; the loss partial and the argmax
-// are reduced with warp shuffles / REDUX, then once across the 8 warps through shared memory.
-// HBM-bound by construction: fused it moves H*W*4 B in (+ H*W*4 B per requested output).
+// One CTA of 256 threads owns one (n,j) map.  Threads are laid out 2-D over the map (a thread keeps
+// one 4-float column group and walks down the rows), so the Gaussian-window test in x and the table
+// column offsets are loop invariants; H*W floats are streamed with 16-byte loads/stores, 4 independent
+// vectors in flight per thread.  The target value is recomputed from the joint (a <=31x31 table in
+// shared memory) instead of being re-read.  The argmax keeps the exact numpy order (first index on
+// ties, NaN is the maximum) but tests one NaN-propagating max of the 4 lanes of a vector against the
+// running best and only then falls into the exact per-element update, so the common case costs four
+// instructions per vector.  Loss partials and the argmax are reduced with warp shuffles / REDUX and
+// once across the 8 warps through shared memory.  The last CTA to finish (ticket) adds the per-map
+// partials in index order (deterministic loss) and, if asked, folds the PCK / EPE counts of the batch
+// into the running metric accumulators -- so a whole step's post-backbone work is ONE launch.
+// HBM-bound by construction: it moves H*W*4 B in (+ H*W*4 B per requested output).
 #include "lh_common.cuh"
 
 namespace lh {
@@ -32,11 +40,17 @@ struct HeatmapParams {
     float* coords;
     float* maxvals;
     int32_t* argidx;
+    unsigned long long* metric_counts;  // fused K5 (nullable)
+    double* metric_sums;
     unsigned int* ticket;       // ws + 0
-    double* partials;           // ws + 16, one per map
+    double* cta_loss;           // ws + 16: one slot per CTA (sum of its maps' squared-error sums, in map order)
+    double* cta_epe;            // per CTA: sum of float32 distances of joints 1..J-2
+    unsigned int* cta_wrong;    // per CTA: number of failed PCK tests
     long long n_maps;
     int J, H, W, HW;
     int joint_stride, side, style, use_weight, subpixel;
+    int pck_mode;
+    float pck_thr;
     float stride_x, stride_y, out_scale;
     float grad_scale;           // 1 / (N*J*HW)
     double loss_scale;          // 0.5 / (N*J*HW)
@@ -90,13 +104,356 @@ __device__ __forceinline__ float target_at(const Window& w, const float* s_tab, 
     return 0.0f;
 }
 
-// TSRC: 0 = no target (decode only), 1 = generate from joints, 2 = read target_in.
-template <bool PRED, int TSRC, bool VEC>
-__global__ void __launch_bounds__(kThreads) heatmap_kernel(const HeatmapParams p) {
+__device__ __forceinline__ float max_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+
+// bbox diagonal exactly as the reference's per-sample Python loop (builtin max/min keep the first
+// element unless a later one compares strictly greater/smaller; float32) -- src/utils/loss.py:122-127
+__device__ __forceinline__ float bbox_diag_seq(const float* g, int J, int gs) {
+    float mxx = g[0], mnx = g[0], mxy = g[1], mny = g[1];
+    for (int j = 1; j < J; ++j) {
+        const float x = g[j * gs], y = g[j * gs + 1];
+        if (x > mxx) mxx = x;
+        if (x < mnx) mnx = x;
+        if (y > mxy) mxy = y;
+        if (y < mny) mny = y;
+    }
+    const float w = __fsub_rn(mxx, mnx), h = __fsub_rn(mxy, mny);
+    return __fsqrt_rn(__fadd_rn(__fmul_rn(w, w), __fmul_rn(h, h)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tail of one map: final argmax -> coordinates (+ sub-pixel / inverse affine), outputs, fused metric
+// record.  Runs on warp 0 (lanes cooperate on the bbox diagonal); `jl` = this lane's ground-truth
+// joint of sample n (lane < J), `gj` = the map's own joint.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void map_tail(const HeatmapParams& p, long long m, const float* pred, int bi, float mv,
+                                         bool do_metric, float2 jl, float2 jfirst, float2 gj, int lane,
+                                         double& epe_acc, unsigned int& wrong_acc) {
+    float diag = 0.f;
+    if (do_metric && p.pck_mode == LH_PCK_PROPORTION) {
+        // builtin max()/min() of the reference keep the first element unless a later one compares strictly
+        // greater / smaller: a NaN survives only as the first joint -> NaN-ignoring reduce, then patch.
+        const float nan = __int_as_float(0x7fc00000);
+        float mxx = nan, mnx = nan, mxy = nan, mny = nan;
+        if (p.J <= 32) {
+            if (lane < p.J) { mxx = mnx = jl.x; mxy = mny = jl.y; }
+        } else {
+            const float* g = p.joints + (m / p.J) * p.J * p.joint_stride;
+            for (int j = lane; j < p.J; j += 32) {
+                const float x = g[j * p.joint_stride], y = g[j * p.joint_stride + 1];
+                mxx = fmaxf(mxx, x); mnx = fminf(mnx, x); mxy = fmaxf(mxy, y); mny = fminf(mny, y);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+            mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+            mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+            mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+        }
+        if (jfirst.x != jfirst.x) { mxx = jfirst.x; mnx = jfirst.x; }
+        if (jfirst.y != jfirst.y) { mxy = jfirst.y; mny = jfirst.y; }
+        const float w = __fsub_rn(mxx, mnx), h = __fsub_rn(mxy, mny);
+        diag = __fsqrt_rn(__fadd_rn(__fmul_rn(w, w), __fmul_rn(h, h)));
+    }
+    if (lane != 0) return;
+    const int iy = bi / p.W, ix = bi - iy * p.W;
+    float cx = (float)ix, cy = (float)iy;
+    if (!(mv > 0.0f)) { cx = 0.f; cy = 0.f; }       // loss.py:350-354 (NaN > 0 is false)
+    if (p.subpixel) {
+        // upstream HRNet get_final_preds: px = floor(x + .5)
+        const int px = (int)floorf(cx + 0.5f), py = (int)floorf(cy + 0.5f);
+        if (px > 1 && px < p.W - 1 && py > 1 && py < p.H - 1) {
+            const float dx = __fsub_rn(pred[py * p.W + px + 1], pred[py * p.W + px - 1]);
+            const float dy = __fsub_rn(pred[(py + 1) * p.W + px], pred[(py - 1) * p.W + px]);
+            cx += (dx > 0.f) ? 0.25f : ((dx < 0.f) ? -0.25f : (dx == dx ? 0.f : dx));
+            cy += (dy > 0.f) ? 0.25f : ((dy < 0.f) ? -0.25f : (dy == dy ? 0.f : dy));
+        }
+    }
+    cx = __fmul_rn(cx, p.out_scale);
+    cy = __fmul_rn(cy, p.out_scale);
+    if (p.inv_affine) {
+        const double* A = p.inv_affine + (m / p.J) * 6;
+        const double x = (double)cx, y = (double)cy;
+        const double ox = __dadd_rn(__dadd_rn(__dmul_rn(A[0], x), __dmul_rn(A[1], y)), A[2]);
+        const double oy = __dadd_rn(__dadd_rn(__dmul_rn(A[3], x), __dmul_rn(A[4], y)), A[5]);
+        cx = (float)ox; cy = (float)oy;
+    }
+    p.coords[2 * m] = cx;
+    p.coords[2 * m + 1] = cy;
+    if (p.maxvals) p.maxvals[m] = mv;
+    if (p.argidx) p.argidx[m] = bi;
+    if (do_metric) {
+        // PCK_2d_loss / EPE_train on this joint: float32, no FMA contraction, IEEE sqrt and divide
+        const float dx = __fsub_rn(gj.x, cx), dy = __fsub_rn(gj.y, cy);
+        const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+        const float cmp = (p.pck_mode == LH_PCK_PROPORTION) ? __fdiv_rn(d, diag) : d;
+        wrong_acc += (cmp > p.pck_thr) ? 1u : 0u;
+        // EPE_train keeps joints 1 .. J-2 (range(1, len(distance)) drops the last one too)
+        const int j = (int)(m % p.J);
+        if (j >= 1 && j <= p.J - 2) epe_acc += (double)d;
+    }
+}
+
+// Every CTA leaves one slot (its maps' sums, accumulated in map order); the last CTA to finish adds the
+// slots in index order -- deterministic for a given grid -- and folds the batch's PCK / EPE counts into
+// the running accumulators.
+template <bool DO_LOSS>
+__device__ __forceinline__ void final_reduce(const HeatmapParams& p, bool do_metric, double* s_a, double* s_b,
+                                             unsigned int* s_c, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    double s = 0.0, es = 0.0;
+    unsigned int wrong = 0;
+    for (unsigned int i = tid; i < gridDim.x; i += kThreads) {   // <= 3 rounds: the grid is at most SMs x 4 CTAs
+        if (DO_LOSS) s += __ldcg(p.cta_loss + i);
+        if (do_metric) { wrong += __ldcg(p.cta_wrong + i); es += __ldcg(p.cta_epe + i); }
+    }
+    s = warp_sum(s);
+    es = warp_sum(es);
+    wrong = __reduce_add_sync(0xffffffffu, wrong);
+    if (lane == 0) { s_a[warp] = s; s_b[warp] = es; s_c[warp] = wrong; }
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0, etot = 0.0;
+        unsigned int wtot = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / kWarp; ++w) { tot += s_a[w]; etot += s_b[w]; wtot += s_c[w]; }
+        if (DO_LOSS) {
+            const double loss = tot * p.loss_scale;
+            if (p.loss_f64) *p.loss_f64 = loss;
+            if (p.loss_f32) *p.loss_f32 = (float)loss;
+            if (p.loss_meter) {  // AverageMeter.update(loss.item(), batch_size): float32 loss, stream-ordered
+                const double nb = (double)(p.n_maps / p.J);
+                p.loss_meter[0] += (double)(float)loss * nb;
+                p.loss_meter[1] += nb;
+            }
+        }
+        if (do_metric) {
+            const unsigned long long N = (unsigned long long)(p.n_maps / p.J);
+            const unsigned long long epe_cnt = p.J >= 3 ? N * (unsigned long long)(p.J - 2) : 0ull;
+            atomicAdd(p.metric_counts + 0, (unsigned long long)wtot);
+            atomicAdd(p.metric_counts + 1, (unsigned long long)p.n_maps);
+            atomicAdd(p.metric_counts + 2, epe_cnt);
+            atomicAdd(p.metric_counts + 3, N);
+            atomicAdd(p.metric_sums + 0, etot);
+        }
+        *p.ticket = 0u;  // leave the workspace clean for the next launch
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Vectorised persistent kernel.  TSRC: 0 = no target (decode only), 1 = generate from joints, 2 = read
+// target_in.  Each CTA walks maps m = blockIdx.x, += gridDim.x; per map two barriers:
+//   A  after the streaming pass: per-warp loss partial + NaN-propagating maximum
+//   B  after the winner search: smallest index holding the maximum (numpy's first-index tie-break)
+// Warp 0 then finishes the map (coordinates, outputs, metric record) while the other warps are already
+// streaming the next one; reduction scratch is double-buffered by iteration parity.
+// ------------------------------------------------------------------------------------------------
+template <bool PRED, int TSRC, bool WGT>
+__global__ void __launch_bounds__(kThreads, TSRC == 2 ? 2 : 4) heatmap_vec_kernel(const HeatmapParams p) {
+    __shared__ float s_tab[TSRC == 1 ? kMaxTable : 1];
+    __shared__ double s_sum[2][kThreads / kWarp];
+    __shared__ float s_max[2][kThreads / kWarp];
+    __shared__ int s_idx[2][kThreads / kWarp];
+    __shared__ double s_fin[kThreads / kWarp];
+    __shared__ unsigned int s_finc[kThreads / kWarp];
+    __shared__ int s_last;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    if (TSRC == 1) {
+        for (int i = tid; i < p.side * p.side; i += kThreads) s_tab[i] = p.table[i];
+        __syncthreads();
+    }
+    const bool do_loss = PRED && TSRC != 0;
+    const bool do_dec = PRED && p.coords != nullptr;
+    const bool do_metric = do_dec && p.metric_counts != nullptr;
+
+    constexpr int U = 4;
+    const int vw = p.W >> 2;                 // vectors per row (<= 256, checked by the launcher)
+    const int rp = kThreads / vw;            // rows per pass
+    const int r0 = tid / vw, c = tid - r0 * vw;
+    const int x = 4 * c;
+    const bool active = r0 < rp;
+    const float ninf = __int_as_float(0xff800000);
+
+    double cta_loss = 0.0, cta_epe = 0.0;    // live in thread 0
+    unsigned int cta_wrong = 0;
+    int par = 0;
+    for (long long m = blockIdx.x; m < p.n_maps; m += gridDim.x, par ^= 1) {
+        Window win;
+        win.valid = 0; win.ulx = win.uly = win.brx = win.bry = 0;
+        float2 gj = make_float2(0.f, 0.f), jl = gj, jfirst = gj;
+        if (TSRC == 1 || do_metric) {
+            const float* jp = p.joints + m * p.joint_stride;
+            gj = make_float2(jp[0], jp[1]);
+        }
+        if (TSRC == 1) {
+            win = joint_window(p, m);
+            if (!win.valid) { win.ulx = win.uly = 0; win.brx = win.bry = 0; }
+            if (p.weight_out && tid == 0) p.weight_out[m] = win.valid ? 1.0f : 0.0f;
+        }
+        if (do_metric && warp == 0 && p.pck_mode == LH_PCK_PROPORTION) {
+            // issue the loads of the sample's joints now; they are consumed in the tail
+            const float* g = p.joints + (m / p.J) * p.J * p.joint_stride;
+            jfirst = make_float2(g[0], g[1]);
+            if (lane < p.J && p.J <= 32) jl = make_float2(g[lane * p.joint_stride], g[lane * p.joint_stride + 1]);
+        }
+        float wgt = 1.0f;
+        if (WGT && p.use_weight) {
+            if (p.weight_in) wgt = p.weight_in[m];
+            else if (TSRC == 1) wgt = win.valid ? 1.0f : 0.0f;
+        }
+        const float gs = WGT ? p.grad_scale * wgt : p.grad_scale;  // grad = (pw - tw) * w / count
+
+        const size_t base = (size_t)m * p.HW;
+        const float* pred = PRED ? p.pred + base : nullptr;
+        const float* tin = (TSRC == 2) ? p.target_in + base : nullptr;
+        float* tout = p.target_out ? p.target_out + base : nullptr;
+        float* grad = p.grad ? p.grad + base : nullptr;
+
+        float acc0 = 0.f, acc1 = 0.f;
+        float tmax = ninf;                       // running maximum of this thread (NaN once one is seen)
+        int tvec = r0 * p.W + x;                 // first element of the vector that holds it
+        if (active) {
+            // loop-invariant x part of the Gaussian window
+            int tx[4];
+            bool xin[4];
+            bool any_x = false;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                tx[k] = x + k - win.ulx;
+                xin[k] = (TSRC == 1) && (x + k >= win.ulx) && (x + k < win.brx);
+                any_x |= xin[k];
+            }
+            for (int y0 = r0; y0 < p.H; y0 += U * rp) {
+                float4 pv[U], tv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int y = y0 + u * rp;
+                    if (y < p.H) {
+                        const size_t e = (size_t)y * p.W + x;
+                        if (PRED) pv[u] = ldg_stream4(pred + e);
+                        if (TSRC == 2) tv[u] = ldg_stream4(tin + e);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int y = y0 + u * rp;
+                    if (y >= p.H) continue;
+                    const int e = y * p.W + x;
+                    float t[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (TSRC == 1) {
+                        if (any_x && y >= win.uly && y < win.bry) {
+                            const float* trow = s_tab + (y - win.uly) * p.side;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) if (xin[k]) t[k] = trow[tx[k]];
+                        }
+                        if (tout) stg_stream4(tout + e, make_float4(t[0], t[1], t[2], t[3]));
+                    } else if (TSRC == 2) {
+                        t[0] = tv[u].x; t[1] = tv[u].y; t[2] = tv[u].z; t[3] = tv[u].w;
+                    }
+                    if (PRED) {
+                        const float v[4] = {pv[u].x, pv[u].y, pv[u].z, pv[u].w};
+                        if (do_loss) {
+                            float d[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) d[k] = WGT ? (v[k] - t[k]) * wgt : (v[k] - t[k]);
+                            acc0 = fmaf(d[0], d[0], acc0); acc1 = fmaf(d[1], d[1], acc1);
+                            acc0 = fmaf(d[2], d[2], acc0); acc1 = fmaf(d[3], d[3], acc1);
+                            if (grad) stg_cs4(grad + e, make_float4(d[0] * gs, d[1] * gs, d[2] * gs, d[3] * gs));
+                        }
+                        if (do_dec) {
+                            // vectors are visited in increasing index order: replace only on "strictly greater",
+                            // or when the first NaN shows up (NaN is numpy's maximum); never once tmax is NaN.
+                            const float vmax = max_nan(max_nan(v[0], v[1]), max_nan(v[2], v[3]));
+                            const bool upd = !(vmax <= tmax) && (tmax == tmax);
+                            tmax = upd ? vmax : tmax;
+                            tvec = upd ? e : tvec;
+                        }
+                    }
+                }
+            }
+        }
+        if (!PRED) continue;
+
+        // ---- barrier A: loss partial + map maximum ------------------------------------------------
+        const double wsum = do_loss ? warp_sum((double)acc0 + (double)acc1) : 0.0;
+        float wmax = tmax;
+        if (do_dec) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) wmax = max_nan(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+        }
+        if (lane == 0) { s_sum[par][warp] = wsum; s_max[par][warp] = wmax; }
+        __syncthreads();
+        int cand = 0x7fffffff;
+        float M = 0.f;
+        if (do_dec) {
+            M = s_max[par][0];
+#pragma unroll
+            for (int w = 1; w < kThreads / kWarp; ++w) M = max_nan(M, s_max[par][w]);
+            const bool mnan = M != M;
+            // threads whose own maximum IS the map maximum look up its first position inside their vector
+            if (active && (mnan ? (tmax != tmax) : (tmax == M))) {
+                const float4 q = *reinterpret_cast<const float4*>(pred + tvec);
+                const float v[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int k = 3; k >= 0; --k) if (mnan ? (v[k] != v[k]) : (v[k] == M)) cand = tvec + k;
+            }
+            cand = __reduce_min_sync(0xffffffffu, cand);
+            if (lane == 0) s_idx[par][warp] = cand;
+        }
+        // ---- barrier B: first index of the maximum ------------------------------------------------
+        __syncthreads();
+        if (warp == 0) {
+            if (do_loss && lane == 0) {
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < kThreads / kWarp; ++w) s += s_sum[par][w];
+                cta_loss += s;
+            }
+            if (do_dec) {
+                int bi = s_idx[par][0];
+#pragma unroll
+                for (int w = 1; w < kThreads / kWarp; ++w) bi = min(bi, s_idx[par][w]);
+                if (bi == 0x7fffffff) bi = 0;   // HW == 0 only; keep a defined value
+                // M is the value at bi (the maximum; NaN if the map holds one) -- no second read of pred
+                map_tail(p, m, pred, bi, M, do_metric, jl, jfirst, gj, lane, cta_epe, cta_wrong);
+            }
+        }
+    }
+
+    if (!PRED) return;
+    if ((do_loss && (p.loss_f64 || p.loss_f32 || p.loss_meter)) || do_metric) {
+        if (tid == 0) {
+            p.cta_loss[blockIdx.x] = cta_loss; p.cta_epe[blockIdx.x] = cta_epe; p.cta_wrong[blockIdx.x] = cta_wrong;
+            __threadfence();
+            const unsigned int t = atomicAdd(p.ticket, 1u);
+            s_last = (t == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            if (do_loss) final_reduce<true>(p, do_metric, s_sum[0], s_fin, s_finc, tid);
+            else final_reduce<false>(p, do_metric, s_sum[0], s_fin, s_finc, tid);
+        }
+    }
+}
+
+// Generic scalar kernel for shapes the vector kernel does not take (W % 4 != 0, unaligned pointers):
+// one CTA per map, exact per-element ordering key.
+template <bool PRED, int TSRC>
+__global__ void __launch_bounds__(kThreads) heatmap_scalar_kernel(const HeatmapParams p) {
     __shared__ float s_tab[TSRC == 1 ? kMaxTable : 1];
     __shared__ double s_sum[kThreads / kWarp];
     __shared__ uint32_t s_key[kThreads / kWarp];
     __shared__ int s_idx[kThreads / kWarp];
+    __shared__ double s_fin[kThreads / kWarp];
+    __shared__ unsigned int s_finc[kThreads / kWarp];
     __shared__ int s_last;
 
     const int tid = threadIdx.x;
@@ -105,11 +462,24 @@ __global__ void __launch_bounds__(kThreads) heatmap_kernel(const HeatmapParams p
 
     Window win;
     win.valid = 0; win.ulx = win.uly = win.brx = win.bry = 0;
+    float2 gj = make_float2(0.f, 0.f), jl = gj, jfirst = gj;
+    const bool do_loss = PRED && TSRC != 0;
+    const bool do_dec = PRED && p.coords != nullptr;
+    const bool do_metric = do_dec && p.metric_counts != nullptr;
+    if (TSRC == 1 || do_metric) {
+        const float* jp = p.joints + m * p.joint_stride;
+        gj = make_float2(jp[0], jp[1]);
+    }
     if (TSRC == 1) {
         for (int i = tid; i < p.side * p.side; i += kThreads) s_tab[i] = p.table[i];
         win = joint_window(p, m);
         if (!win.valid) { win.ulx = win.uly = 0; win.brx = win.bry = 0; }
         __syncthreads();
+    }
+    if (do_metric && warp == 0 && p.pck_mode == LH_PCK_PROPORTION) {
+        const float* g = p.joints + (m / p.J) * p.J * p.joint_stride;
+        jfirst = make_float2(g[0], g[1]);
+        if (lane < p.J && p.J <= 32) jl = make_float2(g[lane * p.joint_stride], g[lane * p.joint_stride + 1]);
     }
     float wgt = 1.0f;
     if (p.use_weight) {
@@ -123,90 +493,36 @@ __global__ void __launch_bounds__(kThreads) heatmap_kernel(const HeatmapParams p
     const float* tin = (TSRC == 2) ? p.target_in + base : nullptr;
     float* tout = p.target_out ? p.target_out + base : nullptr;
     float* grad = p.grad ? p.grad + base : nullptr;
-    const bool do_loss = PRED && TSRC != 0;
-    const bool do_dec = PRED && p.coords != nullptr;
 
-    float acc0 = 0.f, acc1 = 0.f;
+    float acc0 = 0.f;
     uint32_t best_key = 0u;
     int best_idx = 0x7fffffff;
-    const float gs = p.grad_scale * wgt;  // grad = (pw - tw) * w / count
-
-    if (VEC) {
-        constexpr int U = 4;
-        const int nvec = p.HW >> 2;
-        for (int b0 = 0; b0 < nvec; b0 += kThreads * U) {
-            float4 pv[U], tv[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = b0 + u * kThreads + tid;
-                if (PRED && i < nvec) pv[u] = ldg_stream4(pred + 4 * (size_t)i);
-                if (TSRC == 2 && i < nvec) tv[u] = ldg_stream4(tin + 4 * (size_t)i);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = b0 + u * kThreads + tid;
-                if (i >= nvec) continue;
-                const int e = 4 * i;
-                float t[4] = {0.f, 0.f, 0.f, 0.f};
-                if (TSRC == 1) {
-                    const int y = e / p.W, x = e - y * p.W;
-                    if (y >= win.uly && y < win.bry && x + 3 >= win.ulx && x < win.brx) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) t[k] = target_at(win, s_tab, p.side, y, x + k);
-                    }
-                    if (tout) stg_stream4(tout + e, make_float4(t[0], t[1], t[2], t[3]));
-                } else if (TSRC == 2) {
-                    t[0] = tv[u].x; t[1] = tv[u].y; t[2] = tv[u].z; t[3] = tv[u].w;
-                }
-                if (PRED) {
-                    const float v[4] = {pv[u].x, pv[u].y, pv[u].z, pv[u].w};
-                    if (do_loss) {
-                        float d[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) d[k] = (v[k] - t[k]) * wgt;
-                        acc0 = fmaf(d[0], d[0], acc0); acc1 = fmaf(d[1], d[1], acc1);
-                        acc0 = fmaf(d[2], d[2], acc0); acc1 = fmaf(d[3], d[3], acc1);
-                        if (grad) stg_cs4(grad + e, make_float4(d[0] * gs, d[1] * gs, d[2] * gs, d[3] * gs));
-                    }
-                    if (do_dec) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint32_t key = order_key(v[k]);
-                            if (key > best_key) { best_key = key; best_idx = e + k; }
-                        }
-                    }
-                }
-            }
+    const float gs = p.grad_scale * wgt;
+    for (int e = tid; e < p.HW; e += kThreads) {
+        float t = 0.f;
+        if (TSRC == 1) {
+            const int y = e / p.W, x = e - y * p.W;
+            t = target_at(win, s_tab, p.side, y, x);
+            if (tout) tout[e] = t;
+        } else if (TSRC == 2) {
+            t = tin[e];
         }
-    } else {
-        for (int e = tid; e < p.HW; e += kThreads) {
-            float t = 0.f;
-            if (TSRC == 1) {
-                const int y = e / p.W, x = e - y * p.W;
-                t = target_at(win, s_tab, p.side, y, x);
-                if (tout) tout[e] = t;
-            } else if (TSRC == 2) {
-                t = tin[e];
+        if (PRED) {
+            const float v = pred[e];
+            if (do_loss) {
+                const float d = (v - t) * wgt;
+                acc0 = fmaf(d, d, acc0);
+                if (grad) grad[e] = d * gs;
             }
-            if (PRED) {
-                const float v = pred[e];
-                if (do_loss) {
-                    const float d = (v - t) * wgt;
-                    acc0 = fmaf(d, d, acc0);
-                    if (grad) grad[e] = d * gs;
-                }
-                if (do_dec) {
-                    const uint32_t key = order_key(v);
-                    if (key > best_key) { best_key = key; best_idx = e; }
-                }
+            if (do_dec) {
+                const uint32_t key = order_key(v);
+                if (key > best_key) { best_key = key; best_idx = e; }
             }
         }
     }
-
     if (!PRED) return;
 
-    // ---- block reductions ------------------------------------------------------------------
-    double wsum = do_loss ? warp_sum((double)acc0 + (double)acc1) : 0.0;
+    double wsum = do_loss ? warp_sum((double)acc0) : 0.0;
     uint32_t kmax = 0u;
     int imin = 0x7fffffff;
     if (do_dec) {
@@ -215,13 +531,12 @@ __global__ void __launch_bounds__(kThreads) heatmap_kernel(const HeatmapParams p
     }
     if (lane == 0) { s_sum[warp] = wsum; s_key[warp] = kmax; s_idx[warp] = imin; }
     __syncthreads();
-
-    if (tid == 0) {
-        if (do_loss) {
-            double s = 0.0;
+    double cta_loss = 0.0, cta_epe = 0.0;
+    unsigned int cta_wrong = 0;
+    if (warp == 0) {
+        if (do_loss && lane == 0) {
 #pragma unroll
-            for (int w = 0; w < kThreads / kWarp; ++w) s += s_sum[w];
-            p.partials[m] = s;
+            for (int w = 0; w < kThreads / kWarp; ++w) cta_loss += s_sum[w];
         }
         if (do_dec) {
             uint32_t bk = 0u; int bi = 0x7fffffff;
@@ -229,42 +544,14 @@ __global__ void __launch_bounds__(kThreads) heatmap_kernel(const HeatmapParams p
             for (int w = 0; w < kThreads / kWarp; ++w) {
                 if (s_key[w] > bk || (s_key[w] == bk && s_idx[w] < bi)) { bk = s_key[w]; bi = s_idx[w]; }
             }
-            // every element has key >= 1 (only -NaN-free minimum -inf maps to 0x007fffff), so bi is set
-            // unless HW == 0; keep a defined value anyway.
             if (bi == 0x7fffffff) bi = 0;
-            const float mv = pred[bi];
-            const int iy = bi / p.W, ix = bi - iy * p.W;
-            float cx = (float)ix, cy = (float)iy;
-            if (!(mv > 0.0f)) { cx = 0.f; cy = 0.f; }       // loss.py:350-354 (NaN > 0 is false)
-            if (p.subpixel) {
-                // upstream HRNet get_final_preds: px = floor(x + .5)
-                const int px = (int)floorf(cx + 0.5f), py = (int)floorf(cy + 0.5f);
-                if (px > 1 && px < p.W - 1 && py > 1 && py < p.H - 1) {
-                    const float dx = __fsub_rn(pred[py * p.W + px + 1], pred[py * p.W + px - 1]);
-                    const float dy = __fsub_rn(pred[(py + 1) * p.W + px], pred[(py - 1) * p.W + px]);
-                    cx += (dx > 0.f) ? 0.25f : ((dx < 0.f) ? -0.25f : (dx == dx ? 0.f : dx));
-                    cy += (dy > 0.f) ? 0.25f : ((dy < 0.f) ? -0.25f : (dy == dy ? 0.f : dy));
-                }
-            }
-            cx = __fmul_rn(cx, p.out_scale);
-            cy = __fmul_rn(cy, p.out_scale);
-            if (p.inv_affine) {
-                const double* A = p.inv_affine + (m / p.J) * 6;
-                const double x = (double)cx, y = (double)cy;
-                const double ox = __dadd_rn(__dadd_rn(__dmul_rn(A[0], x), __dmul_rn(A[1], y)), A[2]);
-                const double oy = __dadd_rn(__dadd_rn(__dmul_rn(A[3], x), __dmul_rn(A[4], y)), A[5]);
-                cx = (float)ox; cy = (float)oy;
-            }
-            p.coords[2 * m] = cx;
-            p.coords[2 * m + 1] = cy;
-            if (p.maxvals) p.maxvals[m] = mv;
-            if (p.argidx) p.argidx[m] = bi;
+            map_tail(p, m, pred, bi, pred[bi], do_metric, jl, jfirst, gj, lane, cta_epe, cta_wrong);
         }
     }
-
-    // ---- deterministic final loss: the last CTA to finish adds the per-map partials in index order
-    if (do_loss && (p.loss_f64 || p.loss_f32 || p.loss_meter)) {
+    if ((do_loss && (p.loss_f64 || p.loss_f32 || p.loss_meter)) || do_metric) {
+        __syncthreads();
         if (tid == 0) {
+            p.cta_loss[blockIdx.x] = cta_loss; p.cta_epe[blockIdx.x] = cta_epe; p.cta_wrong[blockIdx.x] = cta_wrong;
             __threadfence();
             const unsigned int t = atomicAdd(p.ticket, 1u);
             s_last = (t == gridDim.x - 1);
@@ -272,42 +559,52 @@ __global__ void __launch_bounds__(kThreads) heatmap_kernel(const HeatmapParams p
         __syncthreads();
         if (s_last) {
             __threadfence();
-            double s = 0.0;
-            for (long long i = tid; i < p.n_maps; i += kThreads) s += __ldcg(p.partials + i);
-            s = warp_sum(s);
-            if (lane == 0) s_sum[warp] = s;
-            __syncthreads();
-            if (tid == 0) {
-                double tot = 0.0;
-#pragma unroll
-                for (int w = 0; w < kThreads / kWarp; ++w) tot += s_sum[w];
-                const double loss = tot * p.loss_scale;
-                if (p.loss_f64) *p.loss_f64 = loss;
-                if (p.loss_f32) *p.loss_f32 = (float)loss;
-                if (p.loss_meter) {  // AverageMeter.update(loss.item(), batch_size): float32 loss, stream-ordered
-                    const double nb = (double)(p.n_maps / p.J);
-                    p.loss_meter[0] += (double)(float)loss * nb;
-                    p.loss_meter[1] += nb;
-                }
-                *p.ticket = 0u;  // leave the workspace clean for the next launch
-            }
+            if (do_loss) final_reduce<true>(p, do_metric, s_sum, s_fin, s_finc, tid);
+            else final_reduce<false>(p, do_metric, s_sum, s_fin, s_finc, tid);
         }
     }
+}
+
+// resident CTAs per SM x SM count of the current device, per kernel instantiation (cached)
+template <typename K>
+static int persistent_grid(K kernel, int* cache) {
+    if (*cache > 0) return *cache;
+    int dev = 0, sms = 0, occ = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 0) != cudaSuccess) return 0;
+    if (occ < 1) occ = 1;
+    *cache = sms * occ;
+    return *cache;
+}
+
+template <bool PRED, int TSRC, bool WGT>
+static int launch_vec(const HeatmapParams& p, cudaStream_t st) {
+    static int cache = 0;   // one device model per process (B200); benign race: same value
+    const int cap = persistent_grid(heatmap_vec_kernel<PRED, TSRC, WGT>, &cache);
+    if (cap <= 0) return (int)cudaGetLastError();
+    const unsigned grid = (unsigned)(p.n_maps < (long long)cap ? p.n_maps : (long long)cap);
+    heatmap_vec_kernel<PRED, TSRC, WGT><<<grid, kThreads, 0, st>>>(p);
+    return LH_OK;
 }
 
 template <bool PRED, int TSRC>
 static int launch(const HeatmapParams& p, bool vec, cudaStream_t st) {
     if (p.n_maps == 0) return LH_OK;
     if (p.n_maps > 0x7fffffffLL) return LH_EUNSUPPORTED;
-    dim3 grid((unsigned)p.n_maps), block(kThreads);
-    if (vec) heatmap_kernel<PRED, TSRC, true><<<grid, block, 0, st>>>(p);
-    else     heatmap_kernel<PRED, TSRC, false><<<grid, block, 0, st>>>(p);
+    int rc = LH_OK;
+    if (vec) {
+        rc = (p.use_weight != 0) ? launch_vec<PRED, TSRC, true>(p, st) : launch_vec<PRED, TSRC, false>(p, st);
+        if (rc) return rc;
+    } else {
+        heatmap_scalar_kernel<PRED, TSRC><<<(unsigned)p.n_maps, kThreads, 0, st>>>(p);
+    }
     LH_CHECK_LAUNCH();
     return LH_OK;
 }
 
 static bool can_vec(const HeatmapParams& p) {
-    if ((p.W & 3) != 0) return false;
+    if ((p.W & 3) != 0 || (p.W >> 2) > kThreads) return false;
     const void* ptrs[] = {p.pred, p.target_in, p.target_out, p.grad};
     for (const void* q : ptrs) if (q && !aligned16(q)) return false;
     return true;
@@ -320,8 +617,12 @@ static int check_geom(long long N, int J, int H, int W) {
 }
 
 static void fill_ws(HeatmapParams& p, void* ws) {
-    p.ticket = reinterpret_cast<unsigned int*>(ws);
-    p.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 16);
+    char* b = reinterpret_cast<char*>(ws);
+    p.ticket = reinterpret_cast<unsigned int*>(b);
+    // one slot per CTA; the grid never exceeds n_maps
+    p.cta_loss = reinterpret_cast<double*>(b + 16);
+    p.cta_epe = reinterpret_cast<double*>(b + 16 + 8 * (size_t)p.n_maps);
+    p.cta_wrong = reinterpret_cast<unsigned int*>(b + 16 + 16 * (size_t)p.n_maps);
 }
 
 }  // namespace lh
@@ -330,7 +631,7 @@ using namespace lh;
 
 extern "C" size_t lh_heatmap_ws_bytes(int64_t N, int J) {
     if (N < 0 || J < 0) return 0;
-    return 16 + sizeof(double) * (size_t)N * (size_t)J;
+    return 16 + 24 * (size_t)N * (size_t)J;
 }
 
 extern "C" int lh_gen_targets(const float* joints, int joint_stride, int N, int J, int H, int W,
@@ -393,6 +694,14 @@ extern "C" int lh_heatmap_fused(const lh_heatmap_args* a, lh_stream_t stream) {
     p.joint_stride = a->joint_stride; p.side = a->table_side; p.style = a->style;
     p.use_weight = a->use_target_weight; p.subpixel = a->subpixel;
     p.stride_x = a->stride_x; p.stride_y = a->stride_y; p.out_scale = a->out_scale;
+    if (a->metric_counts || a->metric_sums) {
+        // fused K5 needs the decode, the ground-truth joints and both accumulators
+        if (!a->metric_counts || !a->metric_sums || !a->joints || !a->coords) return LH_ENULL;
+        if (a->joint_stride < 2) return LH_EINVAL;
+        if (a->pck_mode != LH_PCK_PROPORTION && a->pck_mode != LH_PCK_MM) return LH_EINVAL;
+        p.metric_counts = a->metric_counts; p.metric_sums = a->metric_sums;
+        p.pck_mode = a->pck_mode; p.pck_thr = a->pck_thr;
+    }
     const double cnt = (double)a->N * a->J * (double)p.HW;
     p.grad_scale = (float)(1.0 / cnt); p.loss_scale = 0.5 / cnt;
     fill_ws(p, a->ws);

@@ -7,8 +7,8 @@
 //
 // Integer counts must be bit-exact against torch-CPU / numpy, so every arithmetic step that
 // feeds a comparison uses explicit round-to-nearest intrinsics (no FMA contraction), IEEE sqrt
-// and IEEE division.  20*J bytes per image: latency/launch-bound, not bandwidth-bound; one
-// thread owns one sample, counts are warp-reduced and flushed with one atomic per warp.
+// and IEEE division.  20*J bytes per image: latency/launch-bound, not bandwidth-bound; one warp
+// owns one sample (lane = joint), counts are block-reduced and flushed with one atomic per block.
 #include "lh_common.cuh"
 
 namespace lh {
@@ -35,17 +35,52 @@ __device__ __forceinline__ float dist_f32(const float* p, const float* g) {
     return __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
 }
 
+// One warp per sample, one lane per joint (J <= 32; larger J walks in chunks of 32): the 20*J bytes of a
+// sample are two coalesced loads, the bbox extremes are warp reductions, the counts come from ballots.
+// Python's builtin max()/min() keep the first element unless a later one compares strictly greater /
+// smaller, so a NaN survives only if it is the FIRST joint: reduce with NaN-ignoring fmaxf/fminf and
+// put the first joint's NaN back.
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
 __global__ void __launch_bounds__(kMThreads)
 pck_epe_batch_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int gs, long long N, int J,
                      float thr, int mode, int visible, unsigned long long* counts, double* sums) {
-    const long long n = (long long)blockIdx.x * kMThreads + threadIdx.x;
+    __shared__ unsigned s_cnt[kMThreads / 32][3];
+    __shared__ double s_es[kMThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long n = (long long)blockIdx.x * (kMThreads / 32) + warp;
     unsigned wrong = 0, total = 0, ecnt = 0;
     double esum = 0.0;
     if (n < N) {
         const float* g = gt + n * J * gs;
         const float* p = pred + n * J * 2;
-        const float diag = bbox_diag_f32(g, J, gs);
-        for (int j = visible ? 1 : 0; j < J; ++j) {
+        const float nan = __int_as_float(0x7fc00000);
+        float mxx = nan, mnx = nan, mxy = nan, mny = nan;       // NaN is ignored by fmaxf / fminf
+        for (int j0 = 0; j0 < J; j0 += 32) {
+            const int j = j0 + lane;
+            if (j < J) {
+                const float x = g[j * gs], y = g[j * gs + 1];
+                mxx = fmaxf(mxx, x); mnx = fminf(mnx, x); mxy = fmaxf(mxy, y); mny = fminf(mny, y);
+            }
+        }
+        mxx = warp_max_f(mxx); mnx = warp_min_f(mnx); mxy = warp_max_f(mxy); mny = warp_min_f(mny);
+        const float fx = g[0], fy = g[1];
+        if (fx != fx) { mxx = fx; mnx = fx; }
+        if (fy != fy) { mxy = fy; mny = fy; }
+        const float w = __fsub_rn(mxx, mnx), h = __fsub_rn(mxy, mny);
+        const float diag = __fsqrt_rn(__fadd_rn(__fmul_rn(w, w), __fmul_rn(h, h)));
+        for (int j0 = 0; j0 < J; j0 += 32) {
+            const int j = j0 + lane;
+            if (j >= J || (visible && j == 0)) continue;
             float d = dist_f32(p + 2 * j, g + j * gs);
             const float dfull = d;
             bool vis_eq1 = true, vis_ne0 = true;
@@ -64,19 +99,22 @@ pck_epe_batch_kernel(const float* __restrict__ pred, const float* __restrict__ g
             if (j >= 1 && j <= J - 2 && (!visible || vis_ne0)) { esum += (double)dfull; ecnt += 1u; }
         }
     }
-    // warp-aggregate, one atomic per warp per quantity
-    for (int o = 16; o > 0; o >>= 1) {
-        wrong += __shfl_xor_sync(0xffffffffu, wrong, o);
-        total += __shfl_xor_sync(0xffffffffu, total, o);
-        ecnt += __shfl_xor_sync(0xffffffffu, ecnt, o);
-    }
+    wrong = __reduce_add_sync(0xffffffffu, wrong);
+    total = __reduce_add_sync(0xffffffffu, total);
+    ecnt = __reduce_add_sync(0xffffffffu, ecnt);
     esum = warp_sum(esum);
-    if ((threadIdx.x & 31) == 0) {
-        if (wrong) atomicAdd(counts + 0, (unsigned long long)wrong);
-        if (total) atomicAdd(counts + 1, (unsigned long long)total);
-        if (ecnt) { atomicAdd(counts + 2, (unsigned long long)ecnt); atomicAdd(sums + 0, esum); }
+    if (lane == 0) { s_cnt[warp][0] = wrong; s_cnt[warp][1] = total; s_cnt[warp][2] = ecnt; s_es[warp] = esum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned w = 0, t = 0, c = 0;
+        double e = 0.0;
+#pragma unroll
+        for (int i = 0; i < kMThreads / 32; ++i) { w += s_cnt[i][0]; t += s_cnt[i][1]; c += s_cnt[i][2]; e += s_es[i]; }
+        if (w) atomicAdd(counts + 0, (unsigned long long)w);
+        if (t) atomicAdd(counts + 1, (unsigned long long)t);
+        if (c) { atomicAdd(counts + 2, (unsigned long long)c); atomicAdd(sums + 0, e); }
+        if (blockIdx.x == 0) atomicAdd(counts + 3, (unsigned long long)N);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(counts + 3, (unsigned long long)N);
 }
 
 __global__ void __launch_bounds__(kMThreads)
@@ -139,7 +177,7 @@ extern "C" int lh_pck_epe_batch(const float* pred_xy, const float* gt, int gt_st
     if (visible && gt_stride < 3) return LH_EINVAL;
     if (mode != LH_PCK_PROPORTION && mode != LH_PCK_MM) return LH_EINVAL;
     if (N == 0) return LH_OK;
-    const long long blocks = (N + kMThreads - 1) / kMThreads;
+    const long long blocks = (N + kMThreads / 32 - 1) / (kMThreads / 32);
     if (blocks > 0x7fffffffLL) return LH_EUNSUPPORTED;
     pck_epe_batch_kernel<<<(unsigned)blocks, kMThreads, 0, (cudaStream_t)stream>>>(
         pred_xy, gt, gt_stride, N, J, thr_f32, mode, visible, counts, sums);

@@ -3,8 +3,8 @@
 //
 // Two slots are double-buffered so the H2D copy of step i+1 (copy stream, DMA engine) overlaps
 // the kernels of step i (compute stream); ordering is by CUDA events only, the host blocks once
-// per step on the slot's "done" event.  Kernels per step: K1 warp+normalise, fused K2+K3+K4,
-// K5 metrics (3 launches; the normalisation table is built once at create time).
+// per step on the slot's "done" event.  Kernels per step: K1 warp+normalise, fused K2+K3+K4+K5
+// (2 launches; the normalisation table is built once at create time).
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -127,7 +127,7 @@ extern "C" int lh_pipeline_create(const lh_pipeline_cfg* cfg, const float* table
     PCHK(cudaMalloc(&p->d_sums, 4 * sizeof(double)));
     PCHK(cudaMemset(p->d_counts, 0, 4 * sizeof(unsigned long long)));
     PCHK(cudaMemset(p->d_sums, 0, 4 * sizeof(double)));
-    rc = lh_norm_lut_build(nullptr, 1, cfg->mean_std, p->d_lut, p->s_comp);
+    rc = lh_norm_lut_build(nullptr, 1, cfg->mean_std, p->d_lut, p->s_comp);   // used when cfg.exact_norm
     if (rc) goto fail;
     PCHK(cudaStreamSynchronize(p->s_comp));
     *out = p;
@@ -141,7 +141,7 @@ extern "C" float* lh_pipeline_input_dev(lh_pipeline* p) { return p ? p->d_input 
 extern "C" float* lh_pipeline_pred_dev(lh_pipeline* p) { return p ? p->d_pred : nullptr; }
 extern "C" float* lh_pipeline_grad_dev(lh_pipeline* p) { return p ? p->d_grad : nullptr; }
 extern "C" float* lh_pipeline_target_dev(lh_pipeline* p) { return p ? p->d_target : nullptr; }
-extern "C" int lh_pipeline_launches_per_step(const lh_pipeline*) { return 3; }
+extern "C" int lh_pipeline_launches_per_step(const lh_pipeline*) { return 2; }
 
 extern "C" int lh_pipeline_reset_metrics(lh_pipeline* p) {
     if (!p) return LH_ENULL;
@@ -178,7 +178,8 @@ extern "C" int lh_pipeline_submit(lh_pipeline* p, const lh_pipeline_io* io, int*
     PCHK(cudaStreamWaitEvent(p->s_comp, s.ev_h2d, 0));
 
     rc = lh_warp_normalize(s.d_images, (int64_t)img_bytes, c.src_h, c.src_w, c.src_w * 3, s.d_affine,
-                           io->flip ? s.d_flip : nullptr, nullptr, c.mean_std, p->d_lut, c.interp, LH_CHAN_RGB,
+                           io->flip ? s.d_flip : nullptr, nullptr, c.mean_std,
+                           (c.exact_norm || c.interp != LH_INTERP_CV2_U8) ? p->d_lut : nullptr, c.interp, LH_CHAN_RGB,
                            LH_LAYOUT_CHW, p->d_input, (int)N, c.out_h, c.out_w, p->s_comp);
     if (rc) goto fail;
     {
@@ -190,12 +191,11 @@ extern "C" int lh_pipeline_submit(lh_pipeline* p, const lh_pipeline_io* io, int*
         a.style = LH_TARGET_HRNET; a.use_target_weight = 0; a.subpixel = c.subpixel;
         a.stride_x = (float)c.out_w / (float)c.W; a.stride_y = (float)c.out_h / (float)c.H;
         a.out_scale = a.stride_x;
+        a.metric_counts = p->d_counts; a.metric_sums = p->d_sums;      // K5 folded into the same launch
+        a.pck_thr = c.pck_T; a.pck_mode = LH_PCK_PROPORTION;
         rc = lh_heatmap_fused(&a, p->s_comp);
         if (rc) goto fail;
     }
-    rc = lh_pck_epe_batch(s.d_coords, s.d_joints, 2, (int64_t)N, c.J, c.pck_T, LH_PCK_PROPORTION, 0,
-                          p->d_counts, p->d_sums, p->s_comp);
-    if (rc) goto fail;
     PCHK(cudaMemcpyAsync(s.h_out, s.d_loss, sizeof(float), cudaMemcpyDeviceToHost, p->s_comp));
     if (io->coords) PCHK(cudaMemcpyAsync(s.h_out + p->off_coords, s.d_coords, N * J * 2 * sizeof(float), cudaMemcpyDeviceToHost, p->s_comp));
     if (io->maxvals) PCHK(cudaMemcpyAsync(s.h_out + p->off_maxvals, s.d_maxvals, N * J * sizeof(float), cudaMemcpyDeviceToHost, p->s_comp));

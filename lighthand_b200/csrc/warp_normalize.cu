@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kWThreads) warp_cv2_kernel(const WarpParams p)
     const bool flip = p.flip ? (p.flip[n] != 0) : false;
 
     if (tid == 0) invert_affine(p.M + (long long)n * 6, s_im);
-    if (!F32) {
+    if (!F32 && p.lut) {
         const float* lut = p.lut + (p.lut_per_image ? (size_t)n * 768 : 0);
         for (int i = tid; i < 768; i += kWThreads) s_lut[i] = lut[i];
     }
@@ -240,7 +240,8 @@ __global__ void __launch_bounds__(kWThreads) warp_cv2_kernel(const WarpParams p)
                 const int h0 = (int)((a0 >> sft) & 0xff) * wx0 + (int)((b0 >> sft) & 0xff) * ax;
                 const int h1 = (int)((a1 >> sft) & 0xff) * wx0 + (int)((b1 >> sft) & 0xff) * ax;
                 const int v = (h0 * wy0 + h1 * ay + 512) >> 10;
-                out[c][k] = s_lut[c * 256 + v];
+                // table (torch-exact) | one FMA with a, b in mean/stdv | raw 0..255
+                out[c][k] = p.lut ? s_lut[c * 256 + v] : (p.normalise ? fmaf((float)v, p.mean[c], p.stdv[c]) : (float)v);
             }
         } else {
             const float fx = __fmul_rn((float)ax, 0.03125f), fy = __fmul_rn((float)ay, 0.03125f);
@@ -260,6 +261,228 @@ __global__ void __launch_bounds__(kWThreads) warp_cv2_kernel(const WarpParams p)
     }
 
     store_tile(p, out, n, oy, ox);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast uint8 path (LH_INTERP_CV2_U8, 4-byte aligned rows): "pair" staging + IDP.4A.
+//
+// The source footprint of the 32x32 output tile is staged ONCE into shared memory as 8-byte
+// position records  rec[y][x] = { R[x] R[x+1] G[x] G[x+1] | B[x] B[x+1] - - }  (built with PRMT from
+// 32-bit global loads; positions outside the image hold zeros = cv2's constant border).  A bilinear
+// tap pair is then one LDS.64 per source row, and the horizontal blend of a channel is one IDP.4A
+// against the weight word (32-ax, ax, 0, 0) [<< 16 for G] -- no byte unpacking, no funnel shifts, no
+// per-pixel bounds test.  Lane = output column, so the 32 lanes of a tap load walk neighbouring
+// records (bank-conflict free up to the rotation) and every store instruction writes one 128-byte line.
+// The horizontal flip is folded into the coordinate tables exactly:
+//   X' = 32(sw-1) - X  in the 1/32-px fixed-point domain  <=>  X0' = 1024(sw-1) + 31 - X0, adelta' = -adelta.
+// Normalisation: NORM 0 none (0..255), 1 single FMA v*a+b, 2 exact table (torch's three roundings).
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxPos = 3072;  // 24 KB of position records per CTA
+
+__device__ __forceinline__ int clamp_i(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+struct TileBox {       // footprint of one output tile in the source, in staged-record coordinates
+    int lox, hix, loy, hiy;   // clamped tap-origin range (records -2 / sw and rows -2 / sh are all-zero)
+    int cx0, pitch, nrows;    // staged window: columns cx0 .. cx0+pitch-1, rows loy .. loy+nrows-1
+    int flags;                // bit0 staged, bit1 need_clamp, bit2 interior
+};
+
+// footprint too large for the staging buffer (strong down-scaling): the two tap records straight from global
+__device__ __noinline__ uint4 taps_from_global(const uint8_t* img, int pitch_b, int sw, int sh, int ix, int iy) {
+    uint32_t px[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int xx = ix + (t & 1), yy = iy + (t >> 1);
+        uint32_t v = 0;
+        if (xx >= 0 && xx < sw && yy >= 0 && yy < sh) {
+            const uint8_t* q = img + (long long)yy * pitch_b + 3 * xx;
+            v = __ldg(q) | (__ldg(q + 1) << 8) | (__ldg(q + 2) << 16);
+        }
+        px[t] = v;
+    }
+    return make_uint4(__byte_perm(px[0], px[1], 0x5140), __byte_perm(px[0], px[1], 0x0062),
+                      __byte_perm(px[2], px[3], 0x5140), __byte_perm(px[2], px[3], 0x0062));
+}
+
+// cv2's fixed-point coordinate terms for output column x / row y (Appendix A step 2), flip folded in
+__device__ __forceinline__ int col_term(double m, int x) {
+    return clamp_i(sat_i32(__dmul_rn(__dmul_rn(m, (double)x), 1024.0)), -(1 << 30), 1 << 30);
+}
+__device__ __forceinline__ int row_term(double m, double b, int y) {
+    return clamp_i(sat_i32(__dmul_rn(__dadd_rn(__dmul_rn(m, (double)y), b), 1024.0)), -(1 << 30), 1 << 30) + 16;
+}
+
+template <int NORM, bool CLAMP, bool STAGED>
+__device__ __forceinline__ void warp_rows(const WarpParams& p, const TileBox& bx, const uint2* s_rec, const float* s_lut,
+                                          const int* s_x0, const int* s_y0, const uint8_t* img, int ad, int bd,
+                                          int n, int ox, int oy0, int warp) {
+    const int rec_base = -bx.loy * bx.pitch - bx.cx0;
+    const float na0 = p.mean[0], na1 = p.mean[1], na2 = p.mean[2];   // NORM 1: a, b of v*a + b
+    const float nb0 = p.stdv[0], nb1 = p.stdv[1], nb2 = p.stdv[2];
+    const bool bgr = p.chan_order == LH_CHAN_BGR;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int r = warp + 8 * j;                 // tile row handled by this warp in pass j
+        const int oy = oy0 + r;
+        if (oy >= p.oh) break;
+        const int X = (s_x0[r] + ad) >> 5, Y = (s_y0[r] + bd) >> 5;
+        int ix = X >> 5, iy = Y >> 5;
+        const uint32_t ax = X & 31, ay = Y & 31;
+        uint2 t0, t1;
+        if (STAGED) {
+            if (CLAMP) { ix = clamp_i(ix, bx.lox, bx.hix); iy = clamp_i(iy, bx.loy, bx.hiy); }
+            const uint2* q = s_rec + (iy * bx.pitch + ix + rec_base);
+            t0 = q[0]; t1 = q[bx.pitch];
+        } else {
+            const uint4 t = taps_from_global(img, p.pitch, p.sw, p.sh, ix, iy);
+            t0 = make_uint2(t.x, t.y); t1 = make_uint2(t.z, t.w);
+        }
+        const uint32_t wl = ax * 255u + 32u;   // bytes (32-ax, ax, 0, 0)
+        const uint32_t wh = wl << 16;          // bytes (0, 0, 32-ax, ax)
+        const uint32_t wy0 = 32u - ay;
+        const uint32_t vr = (__dp4a(t0.x, wl, 0u) * wy0 + __dp4a(t1.x, wl, 0u) * ay + 512u) >> 10;
+        const uint32_t vg = (__dp4a(t0.x, wh, 0u) * wy0 + __dp4a(t1.x, wh, 0u) * ay + 512u) >> 10;
+        const uint32_t vb = (__dp4a(t0.y, wl, 0u) * wy0 + __dp4a(t1.y, wl, 0u) * ay + 512u) >> 10;
+        float o0, o1, o2;
+        if (NORM == 2) { o0 = s_lut[vr]; o1 = s_lut[256 + vg]; o2 = s_lut[512 + vb]; }
+        else if (NORM == 1) { o0 = fmaf((float)vr, na0, nb0); o1 = fmaf((float)vg, na1, nb1); o2 = fmaf((float)vb, na2, nb2); }
+        else { o0 = (float)vr; o1 = (float)vg; o2 = (float)vb; }
+        if (bgr) { const float t = o0; o0 = o2; o2 = t; }
+        if (p.layout == LH_LAYOUT_CHW) {
+            float* d = p.dst + (((size_t)n * 3) * p.oh + oy) * p.ow + ox;
+            const size_t plane = (size_t)p.oh * p.ow;
+            __stcs(d, o0); __stcs(d + plane, o1); __stcs(d + 2 * plane, o2);
+        } else {
+            float* d = p.dst + (((size_t)n * p.oh + oy) * p.ow + ox) * 3;
+            __stcs(d, o0); __stcs(d + 1, o1); __stcs(d + 2, o2);
+        }
+    }
+}
+
+template <int NORM>
+__global__ void __launch_bounds__(kWThreads) warp_pairs_kernel(const WarpParams p) {
+    __shared__ __align__(16) uint2 s_rec[kMaxPos];
+    __shared__ float s_lut[NORM == 2 ? 768 : 1];
+    __shared__ int s_ad[kTile], s_bd[kTile], s_x0[kTile], s_y0[kTile];
+    __shared__ TileBox s_box;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int n = blockIdx.z;
+    const int tx0 = blockIdx.x * kTile, ty0 = blockIdx.y * kTile;
+    const uint8_t* img = p.src + (long long)n * p.img_stride;
+
+    // ---- phase 1: coordinate tables (warps 0,1) and tile footprint (warp 2, lane 0); every participating
+    // thread inverts the 2x3 matrix itself (a handful of FP64 ops) so there is a single barrier
+    if (warp < 3 && (warp < 2 || lane == 0)) {
+        const bool flip = p.flip ? (p.flip[n] != 0) : false;
+        double im[6];
+        invert_affine(p.M + (long long)n * 6, im);
+        const int mirror = 1024 * (p.sw - 1) + 31;
+        if (warp == 0) {
+            const int a = col_term(im[0], tx0 + lane);
+            s_ad[lane] = flip ? -a : a;
+            s_bd[lane] = col_term(im[3], tx0 + lane);
+        } else if (warp == 1) {
+            const int x0 = row_term(im[1], im[2], ty0 + lane);
+            s_x0[lane] = flip ? mirror - x0 : x0;
+            s_y0[lane] = row_term(im[4], im[5], ty0 + lane);
+        } else {
+            // the maps are monotone in x and in y, so the footprint is spanned by the 4 tile corners
+            const int cl = min(kTile, p.ow - tx0) - 1, rl = min(kTile, p.oh - ty0) - 1;
+            int a0 = col_term(im[0], tx0), a1 = col_term(im[0], tx0 + cl);
+            if (flip) { a0 = -a0; a1 = -a1; }
+            const int b0 = col_term(im[3], tx0), b1 = col_term(im[3], tx0 + cl);
+            int xa = row_term(im[1], im[2], ty0), xb = row_term(im[1], im[2], ty0 + rl);
+            if (flip) { xa = mirror - xa; xb = mirror - xb; }
+            const int ya = row_term(im[4], im[5], ty0), yb = row_term(im[4], im[5], ty0 + rl);
+            const int X00 = (xa + a0) >> 10, X01 = (xa + a1) >> 10, X10 = (xb + a0) >> 10, X11 = (xb + a1) >> 10;
+            const int Y00 = (ya + b0) >> 10, Y01 = (ya + b1) >> 10, Y10 = (yb + b0) >> 10, Y11 = (yb + b1) >> 10;
+            const int ixmin = min(min(X00, X01), min(X10, X11)), ixmax = max(max(X00, X01), max(X10, X11));
+            const int iymin = min(min(Y00, Y01), min(Y10, Y11)), iymax = max(max(Y00, Y01), max(Y10, Y11));
+            TileBox bx;
+            bx.lox = clamp_i(ixmin, -2, p.sw); bx.hix = clamp_i(ixmax, -2, p.sw);
+            bx.loy = clamp_i(iymin, -2, p.sh); bx.hiy = clamp_i(iymax, -2, p.sh);
+            const bool need_clamp = (bx.lox != ixmin) | (bx.hix != ixmax) | (bx.loy != iymin) | (bx.hiy != iymax);
+            bx.cx0 = bx.lox & ~3;                               // staged columns start at a multiple of 4 records
+            bx.pitch = ((bx.hix - bx.cx0 + 1) + 3) & ~3;        // records per staged row
+            bx.nrows = bx.hiy - bx.loy + 2;                     // rows loy .. hiy+1
+            const bool staged = bx.nrows * bx.pitch <= kMaxPos;
+            const bool interior = (bx.loy >= 0) & (bx.loy + bx.nrows <= p.sh) & (bx.cx0 >= 0) &
+                                  (bx.cx0 + bx.pitch + 1 <= p.sw);
+            bx.flags = (staged ? 1 : 0) | (need_clamp ? 2 : 0) | (interior ? 4 : 0);
+            s_box = bx;
+        }
+    }
+    if (NORM == 2) {
+        const float* lut = p.lut + (p.lut_per_image ? (size_t)n * 768 : 0);
+        for (int i = tid; i < 768; i += kWThreads) s_lut[i] = lut[i];
+    }
+    __syncthreads();
+    const TileBox bx = s_box;
+    const bool staged = bx.flags & 1;
+
+    // ---- phase 2: stage the footprint as position records ---------------------------------------------
+    if (staged) {
+        const int gpr = bx.pitch >> 2;                  // groups of 4 records per row
+        const int total = bx.nrows * gpr;               // < 1024
+        const unsigned inv = ((1u << 20) + gpr - 1) / gpr;   // exact floor(g / gpr) for g < 2^10
+        if (bx.flags & 4) {
+            // interior tile: every staged byte lies inside the image, no predicates, no masks
+            const uint8_t* org = img + (long long)bx.loy * p.pitch + 3 * bx.cx0;
+            for (int g = tid; g < total; g += kWThreads) {
+                const int r = (int)((g * inv) >> 20), k = g - r * gpr;
+                const uint32_t* rp = reinterpret_cast<const uint32_t*>(org + (long long)r * p.pitch) + 3 * k;
+                const uint32_t w0 = __ldg(rp), w1 = __ldg(rp + 1), w2 = __ldg(rp + 2), w3 = __ldg(rp + 3);
+                uint4* d = reinterpret_cast<uint4*>(s_rec + r * bx.pitch + 4 * k);
+                d[0] = make_uint4(__byte_perm(w0, w1, 0x4130), __byte_perm(w0, w1, 0x0052),
+                                  __byte_perm(w0, w1, 0x7463), __byte_perm(w1, w2, 0x0041));
+                d[1] = make_uint4(__byte_perm(w1, w2, 0x6352), __byte_perm(w2, w2, 0x0030),
+                                  __byte_perm(w2, w3, 0x5241), __byte_perm(w2, w3, 0x0063));
+            }
+        } else {
+            const int rowb = 3 * p.sw;
+            for (int g = tid; g < total; g += kWThreads) {
+                const int r = (int)((g * inv) >> 20), k = g - r * gpr;
+                const int y = bx.loy + r, x = bx.cx0 + 4 * k;
+                uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+                const bool yin = (y >= 0) & (y < p.sh);
+                const int bo = 3 * x;                // byte offset of the group in the row (multiple of 4)
+                if (yin) {
+                    const uint32_t* rp = reinterpret_cast<const uint32_t*>(img + (long long)y * p.pitch);
+                    // a word is loaded when it starts inside [0, rowb); bytes of it beyond the row are masked below
+                    if (bo >= 0 && bo < rowb) w0 = __ldg(rp + (bo >> 2));
+                    if (bo + 4 >= 0 && bo + 4 < rowb) w1 = __ldg(rp + (bo >> 2) + 1);
+                    if (bo + 8 >= 0 && bo + 8 < rowb) w2 = __ldg(rp + (bo >> 2) + 2);
+                    if (bo + 12 >= 0 && bo + 12 < rowb) w3 = __ldg(rp + (bo >> 2) + 3);
+                }
+                uint32_t a[4] = {__byte_perm(w0, w1, 0x4130), __byte_perm(w0, w1, 0x7463),
+                                 __byte_perm(w1, w2, 0x6352), __byte_perm(w2, w3, 0x5241)};
+                uint32_t c[4] = {__byte_perm(w0, w1, 0x0052), __byte_perm(w1, w2, 0x0041),
+                                 __byte_perm(w2, w2, 0x0030), __byte_perm(w2, w3, 0x0063)};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    // zero the halves that lie outside the image (constant border 0)
+                    const bool va = yin && (x + i >= 0) && (x + i < p.sw);
+                    const bool vb = yin && (x + i + 1 >= 0) && (x + i + 1 < p.sw);
+                    const uint32_t m = (va ? 0x00ff00ffu : 0u) | (vb ? 0xff00ff00u : 0u);
+                    a[i] &= m; c[i] &= m;
+                }
+                uint4* d = reinterpret_cast<uint4*>(s_rec + r * bx.pitch + 4 * k);
+                d[0] = make_uint4(a[0], c[0], a[1], c[1]);
+                d[1] = make_uint4(a[2], c[2], a[3], c[3]);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 3: lane = output column, warp w renders tile rows w, w+8, w+16, w+24 --------------------------
+    const int ox = tx0 + lane;
+    if (ox >= p.ow) return;     // columns right of the image edge lie outside the staged footprint
+    const int ad = s_ad[lane], bd = s_bd[lane];
+    if (!staged)            warp_rows<NORM, false, false>(p, bx, s_rec, s_lut, s_x0, s_y0, img, ad, bd, n, ox, ty0, warp);
+    else if (bx.flags & 2)  warp_rows<NORM, true, true>(p, bx, s_rec, s_lut, s_x0, s_y0, img, ad, bd, n, ox, ty0, warp);
+    else                    warp_rows<NORM, false, true>(p, bx, s_rec, s_lut, s_x0, s_y0, img, ad, bd, n, ox, ty0, warp);
 }
 
 // LH_INTERP_TORCH: ToTensor -> Resize(bilinear, align_corners=False, no antialias) -> Normalize.
@@ -326,6 +549,15 @@ __global__ void norm_lut_kernel(const double* gain, int tables, int normalise, f
 
 using namespace lh;
 
+// v*a + b with a = 1/(255 std), b = -mean/std, rounded once from double; stored in p.mean / p.stdv
+static void fma_coeffs(WarpParams& p, const float* mean_std) {
+    for (int i = 0; i < 3; ++i) {
+        const double sd = (double)mean_std[3 + i];
+        p.mean[i] = (float)(1.0 / (255.0 * sd));
+        p.stdv[i] = (float)(-(double)mean_std[i] / sd);
+    }
+}
+
 extern "C" int lh_norm_lut_build(const double* chan_gain, int N, const float* mean_std, float* lut,
                                  lh_stream_t stream) {
     if (!lut) return LH_ENULL;
@@ -353,7 +585,7 @@ extern "C" int lh_warp_normalize(const uint8_t* src, int64_t src_img_stride, int
     if (chan_order != LH_CHAN_RGB && chan_order != LH_CHAN_BGR) return LH_EINVAL;
     if (out_layout != LH_LAYOUT_CHW && out_layout != LH_LAYOUT_HWC) return LH_EINVAL;
     if (interp != LH_INTERP_TORCH && !fwd_affine) return LH_ENULL;
-    if (interp == LH_INTERP_CV2_U8 && !lut) return LH_ENULL;
+    if (interp == LH_INTERP_CV2_U8 && chan_gain && !lut) return LH_ENULL;  // per-image gain needs the table
     if (N == 0) return LH_OK;
     if (N > 65535) return LH_EUNSUPPORTED;  // gridDim.z; callers chunk larger batches
 
@@ -372,7 +604,18 @@ extern "C" int lh_warp_normalize(const uint8_t* src, int64_t src_img_stride, int
         resize_torch_kernel<<<grid, block, 0, st>>>(p);
     } else {
         const bool stage = aligned16(src) && (src_pitch % 16 == 0) && (src_img_stride % 16 == 0);
-        if (interp == LH_INTERP_CV2_U8) {
+        const bool words = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)src_pitch | (uintptr_t)src_img_stride) & 3u) == 0;
+        if (interp == LH_INTERP_CV2_U8 && words) {
+            if (lut) {
+                warp_pairs_kernel<2><<<grid, block, 0, st>>>(p);
+            } else if (mean_std) {
+                fma_coeffs(p, mean_std);
+                warp_pairs_kernel<1><<<grid, block, 0, st>>>(p);
+            } else {
+                warp_pairs_kernel<0><<<grid, block, 0, st>>>(p);
+            }
+        } else if (interp == LH_INTERP_CV2_U8) {
+            if (!lut && mean_std) fma_coeffs(p, mean_std);
             if (stage) warp_cv2_kernel<false, true><<<grid, block, 0, st>>>(p);
             else       warp_cv2_kernel<false, false><<<grid, block, 0, st>>>(p);
         } else {

@@ -113,9 +113,15 @@ def warp_normalize(images_u8: torch.Tensor, fwd_affine: Optional[torch.Tensor], 
                    flip: Optional[torch.Tensor] = None, chan_gain: Optional[torch.Tensor] = None,
                    mean=IMAGENET_MEAN, std=IMAGENET_STD, lut: Optional[torch.Tensor] = None,
                    interp: int = LH_INTERP_CV2_U8, chan_order: int = LH_CHAN_RGB,
-                   layout: int = LH_LAYOUT_CHW, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   layout: int = LH_LAYOUT_CHW, out: Optional[torch.Tensor] = None,
+                   exact_norm: bool = True) -> torch.Tensor:
     """K1.  images_u8 [N,Hs,Ws,3] uint8 CUDA; fwd_affine [N,2,3] float64 (src->dst, as cv2.warpAffine
-    takes it); returns float32 [N,3,oh,ow] (CHW) or [N,oh,ow,3] (HWC)."""
+    takes it); returns float32 [N,3,oh,ow] (CHW) or [N,oh,ow,3] (HWC).
+
+    The warped uint8 pixel is always cv2's, bit for bit.  ``exact_norm=True`` maps it through a table
+    holding torch's float32 ``((v/255) - mean)/std`` (three roundings, bit-identical to
+    ToTensor+Normalize); ``exact_norm=False`` uses one fused multiply-add ``v*a + b`` (within 2 ulp of the
+    former, i.e. ~1e-7 relative against the path's 1e-5 tolerance) and needs no table."""
     require_cuda()
     lib = _lib.load()
     images_u8 = _dev(images_u8, torch.uint8, "images")
@@ -131,8 +137,10 @@ def warp_normalize(images_u8: torch.Tensor, fwd_affine: Optional[torch.Tensor], 
         flip = _dev(flip, torch.uint8, "flip")
     if chan_gain is not None:
         chan_gain = _dev(chan_gain, torch.float64, "chan_gain")
-    if interp == LH_INTERP_CV2_U8 and lut is None:
+    if interp == LH_INTERP_CV2_U8 and lut is None and (exact_norm or chan_gain is not None) and mean is not None:
         lut = build_norm_lut(mean, std, chan_gain, images_u8.device)
+    if interp == LH_INTERP_CV2_U8 and lut is None and chan_gain is not None:
+        lut = build_norm_lut(None, None, chan_gain, images_u8.device)
     if lut is not None:
         lut = _dev(lut, torch.float32, "lut")
     shape = (n, 3, oh, ow) if layout == LH_LAYOUT_CHW else (n, oh, ow, 3)
@@ -251,10 +259,14 @@ def heatmap_fused(pred: torch.Tensor, joints: Optional[torch.Tensor] = None, *,
                   style: int = LH_TARGET_HRNET, want_target: bool = False, want_grad: bool = True,
                   want_decode: bool = True, out_scale: float = 4.0, subpixel: bool = False,
                   inv_affine: Optional[torch.Tensor] = None, use_target_weight: bool = False,
-                  loss_meter: Optional[torch.Tensor] = None, buffers: Optional[dict] = None) -> dict:
+                  loss_meter: Optional[torch.Tensor] = None, buffers: Optional[dict] = None,
+                  metrics: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, pck_T: float = 0.2,
+                  pck_threshold: str = "proportion") -> dict:
     """Fused K2+K3+K4: one read of ``pred`` gives loss, grad, target (optional) and decode.
     ``buffers`` may carry preallocated outputs (keys: target, grad, loss, coords, maxvals, argidx, weight)
-    so the call is allocation-free (CUDA-graph capturable)."""
+    so the call is allocation-free (CUDA-graph capturable).  ``metrics=(counts, sums)`` (see
+    ``new_metric_state``) additionally folds PCK_2d_loss(T, threshold) + EPE_train of the decoded joints
+    against ``joints`` into the accumulators inside the same launch (K5 fused)."""
     require_cuda()
     lib = _lib.load()
     pred = _dev(pred, torch.float32, "pred")
@@ -266,6 +278,10 @@ def heatmap_fused(pred: torch.Tensor, joints: Optional[torch.Tensor] = None, *,
     if target_in is not None:
         target_in = _dev(target_in, torch.float32, "target")
         a.target_in = target_in.data_ptr()
+        if joints is not None:
+            joints = _dev(joints, torch.float32, "joints")
+            a.joints = joints.data_ptr()
+            a.joint_stride = joints.shape[2]
     else:
         if joints is None:
             raise LighthandError("heatmap_fused: joints or target_in required")
@@ -305,6 +321,12 @@ def heatmap_fused(pred: torch.Tensor, joints: Optional[torch.Tensor] = None, *,
     a.subpixel = int(bool(subpixel))
     a.stride_x, a.stride_y = float(feat_stride[0]), float(feat_stride[1])
     a.out_scale = float(out_scale)
+    if metrics is not None:
+        if joints is None or not want_decode:
+            raise LighthandError("heatmap_fused: fused metrics need joints and the decode")
+        a.metric_counts = _dev(metrics[0], torch.int64, "counts").data_ptr()
+        a.metric_sums = _dev(metrics[1], torch.float64, "sums").data_ptr()
+        a.pck_mode, a.pck_thr = _pck_mode(pck_T, pck_threshold)
     with torch.cuda.device(dev):
         ws = b.get("ws")
         if ws is None:
@@ -317,6 +339,15 @@ def heatmap_fused(pred: torch.Tensor, joints: Optional[torch.Tensor] = None, *,
 # ---------------------------------------------------------------------------------------------
 # K5
 # ---------------------------------------------------------------------------------------------
+
+def _pck_mode(T: float, threshold: str):
+    """(mode, float32 threshold) as torch compares it: T for 'proportion', T*3.78 for 'mm' (loss.py:138,144)."""
+    if threshold == "proportion":
+        return LH_PCK_PROPORTION, float(np.float32(T))
+    if threshold == "mm":
+        return LH_PCK_MM, float(np.float32(T * 3.78))
+    raise AssertionError("Please check variable threshold is right")
+
 
 def new_metric_state(device) -> Tuple[torch.Tensor, torch.Tensor]:
     """(counts int64[4] = n_wrong, n_total, epe_count, n_images ; sums float64[4] = epe_sum, loss*n, n, -)."""
@@ -333,12 +364,7 @@ def pck_epe_batch(pred_xy: torch.Tensor, gt: torch.Tensor, T: float, threshold: 
     n, j, gs = gt.shape
     if pred_xy.shape[0] != n or pred_xy.shape[1] != j or pred_xy.shape[2] != 2:
         raise LighthandError("pred_2d: expected [N,J,2] matching gt")
-    if threshold == "proportion":
-        mode, thr = LH_PCK_PROPORTION, float(np.float32(T))
-    elif threshold == "mm":
-        mode, thr = LH_PCK_MM, float(np.float32(T * 3.78))
-    else:
-        raise AssertionError("Please check variable threshold is right")
+    mode, thr = _pck_mode(T, threshold)
     counts = _dev(counts, torch.int64, "counts")
     sums = _dev(sums, torch.float64, "sums")
     with torch.cuda.device(gt.device):

@@ -1,7 +1,7 @@
 """The whole hot path as one object.
 
-``HeatmapPipeline``  device-resident step  K1 warp+normalise -> fused K2+K3+K4 (targets, JointsMSELoss
-                     forward+backward, decode) -> K5 PCK/EPE accumulation.  Three kernel launches, no
+``HeatmapPipeline``  device-resident step  K1 warp+normalise -> fused K2+K3+K4+K5 (targets, JointsMSELoss
+                     forward+backward, decode, PCK/EPE accumulation).  Two kernel launches, no
                      allocation, no host synchronisation; optionally replayed from a CUDA graph.  This is
                      what replaces, per iteration, ``__getitem__``/collate + ``JointsMSELoss`` +
                      ``.cpu()`` + ``get_max_preds`` + ``PCK_2d_loss`` + ``EPE_train`` of the reference's
@@ -29,8 +29,9 @@ class HeatmapPipeline:
                  sigma: float = 2, interp: int = ops.LH_INTERP_CV2_U8, train: bool = True,
                  materialize_target: bool = False, subpixel: bool = False, map_back: bool = False,
                  pck_T: float = 0.2, mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD, device="cuda",
-                 use_graph: bool = False):
+                 use_graph: bool = False, exact_norm: bool = False):
         ops.require_cuda()
+        self.exact_norm = exact_norm
         self.device = torch.device(device)
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
@@ -55,23 +56,22 @@ class HeatmapPipeline:
             self.buffers["grad"] = torch.empty((n, j, h, w), dtype=f32, device=d)
         if materialize_target:
             self.buffers["target"] = torch.empty((n, j, h, w), dtype=f32, device=d)
-        self.lut = ops.build_norm_lut(mean, std, None, d) if interp == ops.LH_INTERP_CV2_U8 else None
+        self.lut = ops.build_norm_lut(mean, std, None, d) if (interp == ops.LH_INTERP_CV2_U8 and exact_norm) else None
         self.meter = DeviceMeter(d)
         self.use_graph = use_graph
         self._graphs = {}
-        self.launches_per_step = 3
+        self.launches_per_step = 2
 
     # -- one step, asynchronous on the current stream -------------------------------------------
     def _enqueue(self, images_u8, fwd_affine, flip, joints, pred, inv_affine):
         ops.warp_normalize(images_u8, fwd_affine, self.out_hw, flip=flip, mean=self.mean, std=self.std,
-                           lut=self.lut, interp=self.interp, out=self.input)
+                           lut=self.lut, interp=self.interp, out=self.input, exact_norm=self.exact_norm)
         ops.heatmap_fused(pred, joints, sigma=self.sigma, feat_stride=self.stride,
                           want_target=self.materialize_target, want_grad=self.train, want_decode=True,
                           out_scale=self.stride[0], subpixel=self.subpixel,
                           inv_affine=inv_affine if self.map_back else None,
-                          loss_meter=self.meter.loss_meter, buffers=self.buffers)
-        ops.pck_epe_batch(self.buffers["coords"], joints, self.pck_T, "proportion", False,
-                          self.meter.counts, self.meter.sums)
+                          loss_meter=self.meter.loss_meter, buffers=self.buffers,
+                          metrics=(self.meter.counts, self.meter.sums), pck_T=self.pck_T)
 
     def step(self, images_u8: torch.Tensor, fwd_affine: Optional[torch.Tensor], joints: torch.Tensor,
              pred: torch.Tensor, flip: Optional[torch.Tensor] = None, inv_affine: Optional[torch.Tensor] = None) -> dict:
@@ -108,8 +108,8 @@ class HeatmapPipeline:
         return out
 
     def prepare(self, images_u8, fwd_affine, joints, pred, flip=None, inv_affine=None) -> "PreparedStep":
-        """Validate and marshal the three C-ABI calls ONCE for a fixed set of device buffers; the returned
-        object's ``launch()`` then costs three raw ctypes calls (no per-step Python argument work), which
+        """Validate and marshal the two C-ABI calls ONCE for a fixed set of device buffers; the returned
+        object's ``launch()`` then costs two raw ctypes calls (no per-step Python argument work), which
         keeps the host ahead of a ~150 us device step without needing a CUDA graph."""
         return PreparedStep(self, images_u8, fwd_affine, joints, pred, flip, inv_affine)
 
@@ -135,7 +135,7 @@ class HeatmapPipeline:
 
 
 class PreparedStep:
-    """Pre-marshalled K1 -> fused -> K5 launch sequence bound to fixed device buffers."""
+    """Pre-marshalled K1 -> fused(K2..K5) launch sequence bound to fixed device buffers."""
 
     def __init__(self, pipe: HeatmapPipeline, images_u8, fwd_affine, joints, pred, flip, inv_affine):
         lib = _lib.load()
@@ -175,9 +175,9 @@ class PreparedStep:
         a.style, a.use_target_weight, a.subpixel = ops.LH_TARGET_HRNET, 0, int(bool(p.subpixel))
         a.stride_x, a.stride_y, a.out_scale = float(p.stride[0]), float(p.stride[1]), float(p.stride[0])
         self._args = a
-        self._k5 = (b["coords"].data_ptr(), joints.data_ptr(), joints.shape[2], p.N, p.J, float(np.float32(p.pck_T)),
-                    ops.LH_PCK_PROPORTION, 0, p.meter.counts.data_ptr(), p.meter.sums.data_ptr())
-        self._f1, self._f2, self._f3 = lib.lh_warp_normalize, lib.lh_heatmap_fused, lib.lh_pck_epe_batch
+        a.metric_counts, a.metric_sums = p.meter.counts.data_ptr(), p.meter.sums.data_ptr()
+        a.pck_mode, a.pck_thr = ops._pck_mode(p.pck_T, "proportion")
+        self._f1, self._f2 = lib.lh_warp_normalize, lib.lh_heatmap_fused
         self._aref = C.byref(a)
 
     def launch(self, stream: Optional[int] = None, events=None) -> None:
@@ -192,7 +192,6 @@ class PreparedStep:
         rc = rc or self._f2(self._aref, st)
         if events is not None:
             events[2].record()
-        rc = rc or self._f3(*self._k5, st)
         if rc:
             check(rc, "prepared step")
 
@@ -204,7 +203,7 @@ class HostPipeline:
     def __init__(self, batch: int, src_hw=(256, 256), out_hw=(256, 256), heatmap_hw=(64, 64), num_joints: int = 21,
                  sigma: float = 2, interp: int = ops.LH_INTERP_CV2_U8, train: bool = True,
                  materialize_target: bool = False, subpixel: bool = False, pck_T: float = 0.2,
-                 mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD, device: int = 0):
+                 mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD, device: int = 0, exact_norm: bool = False):
         ops.require_cuda()
         self.lib = _lib.load()
         cfg = _lib.PipelineCfg()
@@ -214,6 +213,7 @@ class HostPipeline:
         cfg.J, cfg.H, cfg.W = int(num_joints), int(heatmap_hw[0]), int(heatmap_hw[1])
         cfg.interp, cfg.train, cfg.materialize_target = int(interp), int(train), int(materialize_target)
         cfg.subpixel, cfg.sigma, cfg.pck_T = int(subpixel), float(sigma), float(np.float32(pck_T))
+        cfg.exact_norm = int(bool(exact_norm))
         for i, v in enumerate((*mean, *std)):
             cfg.mean_std[i] = float(np.float32(v))
         tmp = int(sigma * 3)

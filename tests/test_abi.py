@@ -26,10 +26,10 @@ def test_header_symbols_are_exported_and_bound():
 
 def test_version_and_error_text():
     lib = _lib.load()
-    assert lib.lh_abi_version() == 1
+    assert lib.lh_abi_version() == 2
     assert b"NULL" in lib.lh_strerror(-2)
     assert lib.lh_strerror(-1).startswith(b"lighthand_b200")
-    assert lib.lh_heatmap_ws_bytes(256, 21) == 16 + 8 * 256 * 21
+    assert lib.lh_heatmap_ws_bytes(256, 21) == 16 + 24 * 256 * 21
 
 
 def test_argument_validation_needs_no_device():
@@ -44,9 +44,9 @@ def test_argument_validation_needs_no_device():
 
 def test_struct_layout_matches_header():
     # offsets the C side relies on: pointers first, then N (int64), then int32s / floats
-    assert ctypes.sizeof(_lib.HeatmapArgs) == 15 * 8 + 8 + 8 * 4 + 3 * 4 + 4   # padded to 8
-    assert _lib.HeatmapArgs.N.offset == 120
-    assert ctypes.sizeof(_lib.PipelineCfg) == 13 * 4 + 2 * 4 + 6 * 4
+    assert ctypes.sizeof(_lib.HeatmapArgs) == 17 * 8 + 8 + 8 * 4 + 4 * 4 + 4 + 4   # 17 pointers, N, 8 int32, 4 float, int32, pad
+    assert _lib.HeatmapArgs.N.offset == 136
+    assert ctypes.sizeof(_lib.PipelineCfg) == 14 * 4 + 2 * 4 + 6 * 4
     assert ctypes.sizeof(_lib.PipelineIO) == 10 * 8
 
 

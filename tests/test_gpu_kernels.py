@@ -164,6 +164,27 @@ def test_fused_equals_separate_kernels(ops):
     assert out3["loss"].item() == lw.item() and torch.equal(out3["grad"], gw)
 
 
+def test_fused_metrics_equal_separate_k5(ops):
+    """K5 folded into the fused launch == lh_pck_epe_batch on the decoded joints (counts bit-exact)."""
+    rng = np.random.default_rng(23)
+    for n, mode, T in ((7, "proportion", 0.2), (33, "mm", 3.0), (256, "proportion", 0.05)):
+        joints = rng.uniform(-10, 266, (n, 21, 2)).astype(np.float32)
+        d_j = cu(joints)
+        tgt, _ = ops.gen_targets(d_j)
+        pred = (tgt + 0.3 * torch.randn_like(tgt)).contiguous()
+        fused = ops.new_metric_state("cuda")
+        for _ in range(2):                                    # accumulates over launches
+            out = ops.heatmap_fused(pred, d_j, metrics=fused, pck_T=T, pck_threshold=mode)
+        sep = ops.new_metric_state("cuda")
+        for _ in range(2):
+            ops.pck_epe_batch(out["coords"], d_j, T, mode, False, *sep)
+        assert fused[0].cpu().tolist() == sep[0].cpu().tolist()
+        assert fused[1][0].item() == pytest.approx(sep[1][0].item(), rel=1e-12)
+        want = R.pck_2d_counts(out["coords"].cpu().numpy(), joints, T, mode)
+        c = fused[0].cpu().tolist()
+        assert (c[1] - c[0], c[1]) == (2 * want[0], 2 * want[1])
+
+
 def test_fused_loss_meter_accumulates_like_average_meter(ops):
     rng = np.random.default_rng(22)
     meter = torch.zeros(2, dtype=torch.float64, device="cuda")

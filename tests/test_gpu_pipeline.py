@@ -70,12 +70,16 @@ def test_device_pipeline_vs_oracle(S, H, sigma, n):
     want = oracle_step(imgs, joints, bbox, scale, rot, flip, pred, S, H, sigma)
 
     for use_graph in (False, True):
-        pipe = HeatmapPipeline(n, (S, S), (S, S), (H, H), sigma=sigma, materialize_target=True, use_graph=use_graph)
+        pipe = HeatmapPipeline(n, (S, S), (S, S), (H, H), sigma=sigma, materialize_target=True, use_graph=use_graph,
+                               exact_norm=not use_graph)
         d = [cu(imgs), cu(trans.astype(np.float64)), cu(joints), cu(pred), cu(flip.astype(np.uint8))]
         for _rep in range(2):
             out = pipe.step(d[0], d[1], d[2], d[3], flip=d[4])
         torch.cuda.synchronize()
-        assert np.abs(out["input"].cpu().numpy() - want["input"]).max() <= 1e-6
+        if use_graph:   # one-FMA normalisation: within 2 ulp of torch's three roundings
+            assert np.abs(out["input"].cpu().numpy() - want["input"]).max() <= 5e-7
+        else:           # table normalisation: bit-identical
+            assert np.array_equal(out["input"].cpu().numpy(), want["input"])
         assert np.array_equal(out["target"].cpu().numpy(), want["target"])
         assert out["loss"].item() == pytest.approx(want["loss"], rel=1e-5)
         np.testing.assert_allclose(out["grad"].cpu().numpy(), want["grad"], rtol=1e-5, atol=1e-12)

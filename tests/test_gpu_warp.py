@@ -53,10 +53,41 @@ def test_warp_normalize_random_augmentations_vs_cv2(ops, src_hw, out_hw):
         flip = bool(rng.uniform() <= 0.5)
         chw, trans, _ = R.warp_normalize_sample(imgs[i], bbox, flip, scale, rot, out_hw)
         Ms.append(trans.astype(np.float64)); flips.append(flip); wants.append(chw)
-    out = ops.warp_normalize(cu(imgs), cu(np.stack(Ms)), out_hw, flip=cu(np.array(flips, np.uint8)))
-    got, want = out.cpu().numpy(), np.stack(wants)
-    lsb = (1 / 255) / min(R.IMAGENET_STD)
-    assert np.abs(got - want).max() <= 1e-6, np.abs(got - want).max() / lsb
+    d_imgs, d_M, d_f = cu(imgs), cu(np.stack(Ms)), cu(np.array(flips, np.uint8))
+    want = np.stack(wants)
+    # exact table normalisation: bit-identical to torch's ToTensor + Normalize of cv2's uint8 pixel
+    got = ops.warp_normalize(d_imgs, d_M, out_hw, flip=d_f, exact_norm=True).cpu().numpy()
+    assert np.array_equal(got, want)
+    # one-FMA normalisation: same uint8 pixel, float result within 2 ulp (values are O(1))
+    fast = ops.warp_normalize(d_imgs, d_M, out_hw, flip=d_f, exact_norm=False).cpu().numpy()
+    assert np.abs(fast - want).max() <= 5e-7
+    # and the raw pixel itself is cv2's, bit for bit, through both code paths
+    raw = ops.warp_normalize(d_imgs, d_M, out_hw, flip=d_f, mean=None, std=None).cpu().numpy()
+    back = np.rint((want * np.array(R.IMAGENET_STD, np.float32)[None, :, None, None]
+                    + np.array(R.IMAGENET_MEAN, np.float32)[None, :, None, None]) * 255)
+    assert np.array_equal(raw, back.astype(np.float32))
+
+
+def test_warp_strong_downscale_falls_back_to_global_taps(ops):
+    """Footprint of a 32x32 tile larger than the staging buffer (4x down-scaling): same pixels."""
+    rng = np.random.default_rng(15)
+    img = rng.integers(0, 256, (1, 512, 512, 3), dtype=np.uint8)
+    M = R.gen_trans_from_patch_cv(256, 256, 480, 480, 64, 64, 1.0, 33.0).astype(np.float64)[None]
+    out = ops.warp_normalize(cu(img), cu(M), (64, 64), mean=None, std=None, layout=ops.LH_LAYOUT_HWC)
+    assert np.array_equal(out[0].cpu().numpy(), R.warp_affine_model(img[0], M[0], 64, 64).astype(np.float32))
+    fl = cu(np.ones(1, np.uint8))
+    out = ops.warp_normalize(cu(img), cu(M), (64, 64), flip=fl, mean=None, std=None, layout=ops.LH_LAYOUT_HWC)
+    assert np.array_equal(out[0].cpu().numpy(), R.warp_affine_model(img[0], M[0], 64, 64, flip=True).astype(np.float32))
+
+
+def test_warp_crop_far_outside_image_is_constant_border(ops):
+    rng = np.random.default_rng(16)
+    img = rng.integers(1, 256, (2, 64, 64, 3), dtype=np.uint8)
+    Ms = np.stack([np.array([[1.0, 0, 500.0], [0, 1.0, -300.0]]), np.array([[1.0, 0, -20.5], [0, 1.0, 40.25]])])
+    out = ops.warp_normalize(cu(img), cu(Ms), (64, 64), mean=None, std=None, layout=ops.LH_LAYOUT_HWC).cpu().numpy()
+    assert float(np.abs(out[0]).max()) == 0.0
+    for i in range(2):
+        assert np.array_equal(out[i], R.warp_affine_model(img[i], Ms[i], 64, 64).astype(np.float32))
 
 
 def test_warp_unaligned_source_uses_unstaged_path(ops):
