@@ -17,6 +17,8 @@
 // partials in index order (deterministic loss) and, if asked, folds the PCK / EPE counts of the batch
 // into the running metric accumulators -- so a whole step's post-backbone work is ONE launch.
 // HBM-bound by construction: it moves H*W*4 B in (+ H*W*4 B per requested output).
+#include <cmath>
+
 #include "lh_common.cuh"
 
 namespace lh {
@@ -52,6 +54,7 @@ struct HeatmapParams {
     int pck_mode;
     float pck_thr;
     float stride_x, stride_y, out_scale;
+    float inv_stride_x, inv_stride_y;   // exact reciprocal when the stride is a power of two, else 0
     float grad_scale;           // 1 / (N*J*HW)
     double loss_scale;          // 0.5 / (N*J*HW)
 };
@@ -67,15 +70,19 @@ __device__ __forceinline__ int trunc_i(float v) {
     return __float2int_rz(v);
 }
 
-__device__ __forceinline__ Window joint_window(const HeatmapParams& p, long long m) {
+// x / s in float32, IEEE-rounded; when s is a power of two (the reference's stride 4) the multiplication by
+// the exact reciprocal is the same value bit for bit and skips the division sequence
+__device__ __forceinline__ float div_stride(float v, float s, float inv_s) {
+    return inv_s != 0.f ? __fmul_rn(v, inv_s) : __fdiv_rn(v, s);
+}
+
+__device__ __forceinline__ Window joint_window(const HeatmapParams& p, float jx, float jy) {
     Window w;
-    const float* jp = p.joints + m * p.joint_stride;
-    const float jx = jp[0], jy = jp[1];
     w.valid = 1;
     if (p.style == LH_TARGET_HRNET) {
         // mu = int(joint / stride + 0.5) in float32  (src/tools/dataset.py:178-179)
-        const float fx = __fadd_rn(__fdiv_rn(jx, p.stride_x), 0.5f);
-        const float fy = __fadd_rn(__fdiv_rn(jy, p.stride_y), 0.5f);
+        const float fx = __fadd_rn(div_stride(jx, p.stride_x, p.inv_stride_x), 0.5f);
+        const float fy = __fadd_rn(div_stride(jy, p.stride_y, p.inv_stride_y), 0.5f);
         const int tmp = (p.side - 1) >> 1;
         const int mx = trunc_i(fx), my = trunc_i(fy);
         w.ulx = mx - tmp; w.uly = my - tmp;
@@ -84,7 +91,7 @@ __device__ __forceinline__ Window joint_window(const HeatmapParams& p, long long
         if (w.ulx >= p.W || w.uly >= p.H || w.brx < 0 || w.bry < 0) w.valid = 0;  // dataset.py:183-186
     } else {
         // GenerateHeatmap: p = joint/4; gate on x > 0 only; int() truncation (dataset_loader.py:38-41)
-        const float px = __fdiv_rn(jx, p.stride_x), py = __fdiv_rn(jy, p.stride_y);
+        const float px = div_stride(jx, p.stride_x, p.inv_stride_x), py = div_stride(jy, p.stride_y, p.inv_stride_y);
         const int half = (p.side - 1) >> 1;  // 3*sigma + 1
         if (!(px > 0.0f) || !(py == py)) {
             w.valid = 0; w.ulx = w.uly = w.brx = w.bry = 0;
@@ -247,18 +254,67 @@ __device__ __forceinline__ void final_reduce(const HeatmapParams& p, bool do_met
 
 // ------------------------------------------------------------------------------------------------
 // Vectorised persistent kernel.  TSRC: 0 = no target (decode only), 1 = generate from joints, 2 = read
-// target_in.  Each CTA walks maps m = blockIdx.x, += gridDim.x; per map two barriers:
+// target_in.  FLAGS (compile time, so absent outputs cost nothing): F_GRAD write d loss / d pred,
+// F_TOUT write the target, F_DEC argmax decode, F_WGT per-map weights.
+// Each CTA walks maps m = blockIdx.x, += gridDim.x; per map two barriers:
 //   A  after the streaming pass: per-warp loss partial + NaN-propagating maximum
 //   B  after the winner search: smallest index holding the maximum (numpy's first-index tie-break)
 // Warp 0 then finishes the map (coordinates, outputs, metric record) while the other warps are already
 // streaming the next one; reduction scratch is double-buffered by iteration parity.
 // ------------------------------------------------------------------------------------------------
-template <bool PRED, int TSRC, bool WGT>
+constexpr int F_GRAD = 1, F_TOUT = 2, F_DEC = 4, F_WGT = 8;
+
+template <bool PRED, int TSRC, int FLAGS>
+struct VecBody {
+    static constexpr bool GRAD = (FLAGS & F_GRAD) != 0, TOUT = (FLAGS & F_TOUT) != 0, DEC = (FLAGS & F_DEC) != 0,
+                          WGT = (FLAGS & F_WGT) != 0, LOSS = PRED && TSRC != 0;
+    // one 4-float vector at element offset e of the current map (row y, fixed column group)
+    __device__ static __forceinline__ void run(const float4& pv, const float4& tv, int y, int e, const Window& win,
+                                               const float* s_tab, int side, const int (&tx)[4], const bool (&xin)[4],
+                                               bool any_x, float wgt, float gs, float* tout, float* grad,
+                                               float& acc0, float& acc1, float& tmax, int& tvec) {
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+        if (TSRC == 1) {
+            const unsigned ry = (unsigned)(y - win.uly);
+            if (any_x && ry < (unsigned)(win.bry - win.uly)) {
+                const float* trow = s_tab + ry * side;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (xin[k]) t[k] = trow[tx[k]];
+            }
+            if (TOUT) stg_stream4(tout + e, make_float4(t[0], t[1], t[2], t[3]));
+        } else if (TSRC == 2) {
+            t[0] = tv.x; t[1] = tv.y; t[2] = tv.z; t[3] = tv.w;
+        }
+        if (PRED) {
+            const float v[4] = {pv.x, pv.y, pv.z, pv.w};
+            if (LOSS) {
+                float d[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) d[k] = WGT ? (v[k] - t[k]) * wgt : (v[k] - t[k]);
+                acc0 = fmaf(d[0], d[0], acc0); acc1 = fmaf(d[1], d[1], acc1);
+                acc0 = fmaf(d[2], d[2], acc0); acc1 = fmaf(d[3], d[3], acc1);
+                if (GRAD) stg_cs4(grad + e, make_float4(d[0] * gs, d[1] * gs, d[2] * gs, d[3] * gs));
+            }
+            if (DEC) {
+                // vectors are visited in increasing index order: replace only on "strictly greater", or when
+                // the first NaN shows up (NaN is numpy's maximum); never once tmax is NaN.
+                const float vmax = max_nan(max_nan(v[0], v[1]), max_nan(v[2], v[3]));
+                const bool upd = !(vmax <= tmax) && (tmax == tmax);
+                tmax = upd ? vmax : tmax;
+                tvec = upd ? e : tvec;
+            }
+        }
+    }
+};
+
+template <bool PRED, int TSRC, int FLAGS>
 __global__ void __launch_bounds__(kThreads, TSRC == 2 ? 2 : 4) heatmap_vec_kernel(const HeatmapParams p) {
+    using Body = VecBody<PRED, TSRC, FLAGS>;
+    constexpr bool GRAD = Body::GRAD, TOUT = Body::TOUT, DEC = Body::DEC, WGT = Body::WGT, LOSS = Body::LOSS;
     __shared__ float s_tab[TSRC == 1 ? kMaxTable : 1];
     __shared__ double s_sum[2][kThreads / kWarp];
-    __shared__ float s_max[2][kThreads / kWarp];
-    __shared__ int s_idx[2][kThreads / kWarp];
+    __shared__ __align__(16) float s_max[2][kThreads / kWarp];
+    __shared__ __align__(16) int s_idx[2][kThreads / kWarp];
     __shared__ double s_fin[kThreads / kWarp];
     __shared__ unsigned int s_finc[kThreads / kWarp];
     __shared__ int s_last;
@@ -269,168 +325,171 @@ __global__ void __launch_bounds__(kThreads, TSRC == 2 ? 2 : 4) heatmap_vec_kerne
         for (int i = tid; i < p.side * p.side; i += kThreads) s_tab[i] = p.table[i];
         __syncthreads();
     }
-    const bool do_loss = PRED && TSRC != 0;
-    const bool do_dec = PRED && p.coords != nullptr;
-    const bool do_metric = do_dec && p.metric_counts != nullptr;
+    const bool do_metric = DEC && p.metric_counts != nullptr;
 
     constexpr int U = 4;
-    const int vw = p.W >> 2;                 // vectors per row (<= 256, checked by the launcher)
+    const int W = p.W, H = p.H, side = p.side;
+    const int vw = W >> 2;                   // vectors per row (<= 256, checked by the launcher)
     const int rp = kThreads / vw;            // rows per pass
     const int r0 = tid / vw, c = tid - r0 * vw;
     const int x = 4 * c;
     const bool active = r0 < rp;
+    const int e0 = r0 * W + x;               // first element of this thread, estep elements between its rows
+    const int estep = rp * W;
+    const int G = (H + U * rp - 1) / (U * rp);   // groups of U rows-per-thread in one map
     const float ninf = __int_as_float(0xff800000);
 
-    double cta_loss = 0.0, cta_epe = 0.0;    // live in thread 0
-    unsigned int cta_wrong = 0;
-    int par = 0;
-    for (long long m = blockIdx.x; m < p.n_maps; m += gridDim.x, par ^= 1) {
-        Window win;
-        win.valid = 0; win.ulx = win.uly = win.brx = win.bry = 0;
-        float2 gj = make_float2(0.f, 0.f), jl = gj, jfirst = gj;
-        if (TSRC == 1 || do_metric) {
-            const float* jp = p.joints + m * p.joint_stride;
-            gj = make_float2(jp[0], jp[1]);
-        }
-        if (TSRC == 1) {
-            win = joint_window(p, m);
-            if (!win.valid) { win.ulx = win.uly = 0; win.brx = win.bry = 0; }
-            if (p.weight_out && tid == 0) p.weight_out[m] = win.valid ? 1.0f : 0.0f;
-        }
-        if (do_metric && warp == 0 && p.pck_mode == LH_PCK_PROPORTION) {
-            // issue the loads of the sample's joints now; they are consumed in the tail
-            const float* g = p.joints + (m / p.J) * p.J * p.joint_stride;
-            jfirst = make_float2(g[0], g[1]);
-            if (lane < p.J && p.J <= 32) jl = make_float2(g[lane * p.joint_stride], g[lane * p.joint_stride + 1]);
-        }
-        float wgt = 1.0f;
-        if (WGT && p.use_weight) {
-            if (p.weight_in) wgt = p.weight_in[m];
-            else if (TSRC == 1) wgt = win.valid ? 1.0f : 0.0f;
-        }
-        const float gs = WGT ? p.grad_scale * wgt : p.grad_scale;  // grad = (pw - tw) * w / count
+    __shared__ double s_cta[2];              // running sums of this CTA (thread 0): squared error, EPE distances
+    __shared__ unsigned int s_ctaw;          // failed PCK tests
+    if (tid == 0) { s_cta[0] = 0.0; s_cta[1] = 0.0; s_ctaw = 0u; }
 
-        const size_t base = (size_t)m * p.HW;
-        const float* pred = PRED ? p.pred + base : nullptr;
-        const float* tin = (TSRC == 2) ? p.target_in + base : nullptr;
-        float* tout = p.target_out ? p.target_out + base : nullptr;
-        float* grad = p.grad ? p.grad + base : nullptr;
+    // software pipeline: the loads of work item k+1 (next row group, possibly of the next map) are issued
+    // right after item k's registers are consumed, so they are in flight across the reductions, the barrier
+    // and the tail of the map.  The tail of map i runs after barrier A of map i+1 (one barrier per map).
+    float4 pv[U], tv[U];
+#define LH_ISSUE(MM, GG)                                                                        \
+    {                                                                                           \
+        const size_t base_ = (size_t)(MM) * p.HW + e0 + (GG) * U * estep;                       \
+        const int y_ = r0 + (GG) * U * rp;                                                      \
+        _Pragma("unroll") for (int u = 0; u < U; ++u) {                                         \
+            if (active && y_ + u * rp < H) {                                                    \
+                if (PRED) pv[u] = ldg_stream4(p.pred + base_ + u * estep);                      \
+                if (TSRC == 2) tv[u] = ldg_stream4(p.target_in + base_ + u * estep);            \
+            }                                                                                   \
+        }                                                                                       \
+    }
+    // warp 0: finish map PM (its reductions are visible: a barrier has passed); joints are re-read (L2 hits)
+#define LH_FINISH_PREV(PM, PPAR)                                                                \
+    {                                                                                           \
+        if (LOSS && lane == 0) {                                                                \
+            double sacc = 0.0;                                                                  \
+            _Pragma("unroll") for (int w = 0; w < kThreads / kWarp; ++w) sacc += s_sum[PPAR][w]; \
+            s_cta[0] += sacc;                                                                   \
+        }                                                                                       \
+        if (DEC) {                                                                              \
+            const float4 ma = *reinterpret_cast<const float4*>(&s_max[PPAR][0]);                \
+            const float4 mb = *reinterpret_cast<const float4*>(&s_max[PPAR][4]);                \
+            const float Mp = max_nan(max_nan(max_nan(ma.x, ma.y), max_nan(ma.z, ma.w)),         \
+                                     max_nan(max_nan(mb.x, mb.y), max_nan(mb.z, mb.w)));        \
+            const int4 ia = *reinterpret_cast<const int4*>(&s_idx[PPAR][0]);                    \
+            const int4 ib = *reinterpret_cast<const int4*>(&s_idx[PPAR][4]);                    \
+            int bi = min(min(min(ia.x, ia.y), min(ia.z, ia.w)), min(min(ib.x, ib.y), min(ib.z, ib.w))); \
+            if (bi == 0x7fffffff) bi = 0; /* HW == 0 only */                                    \
+            float2 pgj = make_float2(0.f, 0.f), pjl = pgj, pjfirst = pgj;                       \
+            if (do_metric) {                                                                    \
+                const float* jp_ = p.joints + (PM) * p.joint_stride;                            \
+                pgj = make_float2(jp_[0], jp_[1]);                                              \
+                const float* gp_ = p.joints + ((PM) / p.J) * p.J * p.joint_stride;              \
+                pjfirst = make_float2(gp_[0], gp_[1]);                                          \
+                if (lane < p.J && p.J <= 32) pjl = make_float2(gp_[lane * p.joint_stride], gp_[lane * p.joint_stride + 1]); \
+            }                                                                                   \
+            double epe_ = 0.0; unsigned int wr_ = 0u;                                           \
+            map_tail(p, (PM), p.pred + (size_t)(PM) * p.HW, bi, Mp, do_metric, pjl, pjfirst, pgj, lane, epe_, wr_); \
+            if (lane == 0 && do_metric) { s_cta[1] += epe_; s_ctaw += wr_; }                    \
+        }                                                                                       \
+    }
 
-        float acc0 = 0.f, acc1 = 0.f;
-        float tmax = ninf;                       // running maximum of this thread (NaN once one is seen)
-        int tvec = r0 * p.W + x;                 // first element of the vector that holds it
+    long long m = blockIdx.x, pm = -1;
+    int g = 0, par = 0;
+    if (m < p.n_maps) LH_ISSUE(m, 0)
+
+    // state of the map being streamed
+    int ulx = 0, uly = 0, brx = 0, bry = 0;
+    float wgt = 1.0f, gs = p.grad_scale;
+    float acc0 = 0.f, acc1 = 0.f, tmax = ninf;
+    int tvec = e0;
+
+    while (m < p.n_maps) {
+        if (g == 0) {
+            // ---- per-map setup -------------------------------------------------------------------------
+            ulx = uly = brx = bry = 0;
+            bool valid = false;
+            if (TSRC == 1) {
+                const float* jp = p.joints + m * p.joint_stride;
+                const Window win = joint_window(p, jp[0], jp[1]);
+                valid = win.valid != 0;
+                if (valid) { ulx = win.ulx; uly = win.uly; brx = win.brx; bry = win.bry; }
+                if (p.weight_out && tid == 0) p.weight_out[m] = valid ? 1.0f : 0.0f;
+            }
+            if (WGT) {
+                wgt = 1.0f;
+                if (p.weight_in) wgt = p.weight_in[m];
+                else if (TSRC == 1) wgt = valid ? 1.0f : 0.0f;
+                gs = p.grad_scale * wgt;                         // grad = (pw - tw) * w / count
+            }
+            acc0 = acc1 = 0.f; tmax = ninf; tvec = e0;
+        }
+        // ---- consume the group in registers ----------------------------------------------------------------
         if (active) {
-            // loop-invariant x part of the Gaussian window
+            Window win;
+            win.ulx = ulx; win.uly = uly; win.brx = brx; win.bry = bry; win.valid = 1;
             int tx[4];
-            bool xin[4];
-            bool any_x = false;
+            bool xin[4], any_x = false;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                tx[k] = x + k - win.ulx;
-                xin[k] = (TSRC == 1) && (x + k >= win.ulx) && (x + k < win.brx);
+            for (int k = 0; k < 4; ++k) {                        // x part of the Gaussian window test
+                tx[k] = x + k - ulx;
+                xin[k] = (TSRC == 1) && (x + k >= ulx) && (x + k < brx);
                 any_x |= xin[k];
             }
-            for (int y0 = r0; y0 < p.H; y0 += U * rp) {
-                float4 pv[U], tv[U];
+            const size_t base = (size_t)m * p.HW;
+            float* tout = TOUT ? p.target_out + base : nullptr;
+            float* grad = GRAD ? p.grad + base : nullptr;
+            const int y = r0 + g * U * rp, e = e0 + g * U * estep;
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int y = y0 + u * rp;
-                    if (y < p.H) {
-                        const size_t e = (size_t)y * p.W + x;
-                        if (PRED) pv[u] = ldg_stream4(pred + e);
-                        if (TSRC == 2) tv[u] = ldg_stream4(tin + e);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int y = y0 + u * rp;
-                    if (y >= p.H) continue;
-                    const int e = y * p.W + x;
-                    float t[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (TSRC == 1) {
-                        if (any_x && y >= win.uly && y < win.bry) {
-                            const float* trow = s_tab + (y - win.uly) * p.side;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) if (xin[k]) t[k] = trow[tx[k]];
-                        }
-                        if (tout) stg_stream4(tout + e, make_float4(t[0], t[1], t[2], t[3]));
-                    } else if (TSRC == 2) {
-                        t[0] = tv[u].x; t[1] = tv[u].y; t[2] = tv[u].z; t[3] = tv[u].w;
-                    }
-                    if (PRED) {
-                        const float v[4] = {pv[u].x, pv[u].y, pv[u].z, pv[u].w};
-                        if (do_loss) {
-                            float d[4];
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) d[k] = WGT ? (v[k] - t[k]) * wgt : (v[k] - t[k]);
-                            acc0 = fmaf(d[0], d[0], acc0); acc1 = fmaf(d[1], d[1], acc1);
-                            acc0 = fmaf(d[2], d[2], acc0); acc1 = fmaf(d[3], d[3], acc1);
-                            if (grad) stg_cs4(grad + e, make_float4(d[0] * gs, d[1] * gs, d[2] * gs, d[3] * gs));
-                        }
-                        if (do_dec) {
-                            // vectors are visited in increasing index order: replace only on "strictly greater",
-                            // or when the first NaN shows up (NaN is numpy's maximum); never once tmax is NaN.
-                            const float vmax = max_nan(max_nan(v[0], v[1]), max_nan(v[2], v[3]));
-                            const bool upd = !(vmax <= tmax) && (tmax == tmax);
-                            tmax = upd ? vmax : tmax;
-                            tvec = upd ? e : tvec;
-                        }
-                    }
-                }
-            }
+            for (int u = 0; u < U; ++u)
+                if (y + u * rp < H)
+                    Body::run(pv[u], tv[u], y + u * rp, e + u * estep, win, s_tab, side, tx, xin, any_x, wgt, gs,
+                              tout, grad, acc0, acc1, tmax, tvec);
         }
-        if (!PRED) continue;
+        // ---- issue the next item's loads ---------------------------------------------------------------------
+        long long m2 = m;
+        int g2 = g + 1;
+        if (g2 == G) { g2 = 0; m2 = m + gridDim.x; }
+        if (m2 < p.n_maps) LH_ISSUE(m2, g2)
 
-        // ---- barrier A: loss partial + map maximum ------------------------------------------------
-        const double wsum = do_loss ? warp_sum((double)acc0 + (double)acc1) : 0.0;
-        float wmax = tmax;
-        if (do_dec) {
+        if (g2 == 0 && PRED) {
+            // ---- map finished: warp partials, barrier A, winner search ---------------------------------------
+            float wsum = acc0 + acc1, wmax = tmax;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) wmax = max_nan(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-        }
-        if (lane == 0) { s_sum[par][warp] = wsum; s_max[par][warp] = wmax; }
-        __syncthreads();
-        int cand = 0x7fffffff;
-        float M = 0.f;
-        if (do_dec) {
-            M = s_max[par][0];
-#pragma unroll
-            for (int w = 1; w < kThreads / kWarp; ++w) M = max_nan(M, s_max[par][w]);
-            const bool mnan = M != M;
-            // threads whose own maximum IS the map maximum look up its first position inside their vector
-            if (active && (mnan ? (tmax != tmax) : (tmax == M))) {
-                const float4 q = *reinterpret_cast<const float4*>(pred + tvec);
-                const float v[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                for (int k = 3; k >= 0; --k) if (mnan ? (v[k] != v[k]) : (v[k] == M)) cand = tvec + k;
+            for (int o = 16; o > 0; o >>= 1) {
+                if (LOSS) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+                if (DEC) wmax = max_nan(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
             }
-            cand = __reduce_min_sync(0xffffffffu, cand);
-            if (lane == 0) s_idx[par][warp] = cand;
-        }
-        // ---- barrier B: first index of the maximum ------------------------------------------------
-        __syncthreads();
-        if (warp == 0) {
-            if (do_loss && lane == 0) {
-                double s = 0.0;
+            if (lane == 0) { if (LOSS) s_sum[par][warp] = (double)wsum; if (DEC) s_max[par][warp] = wmax; }
+            __syncthreads();
+            // the barrier also published the previous map's winner indices: warp 0 finishes that map now
+            if (warp == 0 && pm >= 0) LH_FINISH_PREV(pm, par ^ 1)
+            if (DEC) {
+                const float4 ma = *reinterpret_cast<const float4*>(&s_max[par][0]);
+                const float4 mb = *reinterpret_cast<const float4*>(&s_max[par][4]);
+                const float M = max_nan(max_nan(max_nan(ma.x, ma.y), max_nan(ma.z, ma.w)),
+                                        max_nan(max_nan(mb.x, mb.y), max_nan(mb.z, mb.w)));
+                const bool mnan = M != M;
+                int cand = 0x7fffffff;
+                // threads whose own maximum IS the map maximum look up its first position inside their vector
+                if (active && (mnan ? (tmax != tmax) : (tmax == M))) {
+                    const float4 q = *reinterpret_cast<const float4*>(p.pred + (size_t)m * p.HW + tvec);
+                    const float v[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-                for (int w = 0; w < kThreads / kWarp; ++w) s += s_sum[par][w];
-                cta_loss += s;
+                    for (int k = 3; k >= 0; --k) if (mnan ? (v[k] != v[k]) : (v[k] == M)) cand = tvec + k;
+                }
+                cand = __reduce_min_sync(0xffffffffu, cand);
+                if (lane == 0) s_idx[par][warp] = cand;
             }
-            if (do_dec) {
-                int bi = s_idx[par][0];
-#pragma unroll
-                for (int w = 1; w < kThreads / kWarp; ++w) bi = min(bi, s_idx[par][w]);
-                if (bi == 0x7fffffff) bi = 0;   // HW == 0 only; keep a defined value
-                // M is the value at bi (the maximum; NaN if the map holds one) -- no second read of pred
-                map_tail(p, m, pred, bi, M, do_metric, jl, jfirst, gj, lane, cta_epe, cta_wrong);
-            }
+            pm = m;
+            par ^= 1;
         }
+        m = m2; g = g2;
     }
 
     if (!PRED) return;
-    if ((do_loss && (p.loss_f64 || p.loss_f32 || p.loss_meter)) || do_metric) {
+    __syncthreads();                                  // publishes the last map's winner indices
+    if (warp == 0 && pm >= 0) LH_FINISH_PREV(pm, par ^ 1)
+#undef LH_ISSUE
+#undef LH_FINISH_PREV
+    if ((LOSS && (p.loss_f64 || p.loss_f32 || p.loss_meter)) || do_metric) {
         if (tid == 0) {
-            p.cta_loss[blockIdx.x] = cta_loss; p.cta_epe[blockIdx.x] = cta_epe; p.cta_wrong[blockIdx.x] = cta_wrong;
+            p.cta_loss[blockIdx.x] = s_cta[0]; p.cta_epe[blockIdx.x] = s_cta[1]; p.cta_wrong[blockIdx.x] = s_ctaw;
             __threadfence();
             const unsigned int t = atomicAdd(p.ticket, 1u);
             s_last = (t == gridDim.x - 1);
@@ -438,8 +497,7 @@ __global__ void __launch_bounds__(kThreads, TSRC == 2 ? 2 : 4) heatmap_vec_kerne
         __syncthreads();
         if (s_last) {
             __threadfence();
-            if (do_loss) final_reduce<true>(p, do_metric, s_sum[0], s_fin, s_finc, tid);
-            else final_reduce<false>(p, do_metric, s_sum[0], s_fin, s_finc, tid);
+            final_reduce<LOSS>(p, do_metric, s_sum[0], s_fin, s_finc, tid);
         }
     }
 }
@@ -472,7 +530,7 @@ __global__ void __launch_bounds__(kThreads) heatmap_scalar_kernel(const HeatmapP
     }
     if (TSRC == 1) {
         for (int i = tid; i < p.side * p.side; i += kThreads) s_tab[i] = p.table[i];
-        win = joint_window(p, m);
+        win = joint_window(p, gj.x, gj.y);
         if (!win.valid) { win.ulx = win.uly = 0; win.brx = win.bry = 0; }
         __syncthreads();
     }
@@ -578,23 +636,51 @@ static int persistent_grid(K kernel, int* cache) {
     return *cache;
 }
 
-template <bool PRED, int TSRC, bool WGT>
+template <bool PRED, int TSRC, int FLAGS>
 static int launch_vec(const HeatmapParams& p, cudaStream_t st) {
     static int cache = 0;   // one device model per process (B200); benign race: same value
-    const int cap = persistent_grid(heatmap_vec_kernel<PRED, TSRC, WGT>, &cache);
+    const int cap = persistent_grid(heatmap_vec_kernel<PRED, TSRC, FLAGS>, &cache);
     if (cap <= 0) return (int)cudaGetLastError();
     const unsigned grid = (unsigned)(p.n_maps < (long long)cap ? p.n_maps : (long long)cap);
-    heatmap_vec_kernel<PRED, TSRC, WGT><<<grid, kThreads, 0, st>>>(p);
+    heatmap_vec_kernel<PRED, TSRC, FLAGS><<<grid, kThreads, 0, st>>>(p);
     return LH_OK;
 }
 
+// runtime output set -> compile-time FLAGS (only the combinations the entry points can produce)
+template <int TSRC>
+static int dispatch_pred(const HeatmapParams& p, cudaStream_t st) {
+    const bool g = p.grad != nullptr, d = p.coords != nullptr, w = p.use_weight != 0;
+    const bool t = (TSRC == 1) && p.target_out != nullptr;
+#define LH_CASE(G, T, D, Wt)                                                                              \
+    if (g == G && t == T && d == D && w == Wt)                                                            \
+        return launch_vec<true, TSRC, (G ? F_GRAD : 0) | (T ? F_TOUT : 0) | (D ? F_DEC : 0) | (Wt ? F_WGT : 0)>(p, st);
+    if constexpr (TSRC == 0) {
+        LH_CASE(false, false, true, false)
+        return LH_EINVAL;
+    } else {
+    LH_CASE(true, false, true, false)  LH_CASE(true, false, false, false) LH_CASE(false, false, true, false)
+    LH_CASE(false, false, false, false) LH_CASE(true, false, true, true)  LH_CASE(true, false, false, true)
+    LH_CASE(false, false, true, true)  LH_CASE(false, false, false, true)
+    if constexpr (TSRC == 1) {
+        LH_CASE(true, true, true, false)  LH_CASE(true, true, false, false) LH_CASE(false, true, true, false)
+        LH_CASE(false, true, false, false) LH_CASE(true, true, true, true)  LH_CASE(true, true, false, true)
+        LH_CASE(false, true, true, true)  LH_CASE(false, true, false, true)
+    }
+    return LH_EINVAL;
+    }
+#undef LH_CASE
+}
+
 template <bool PRED, int TSRC>
-static int launch(const HeatmapParams& p, bool vec, cudaStream_t st) {
+static int launch(HeatmapParams& p, bool vec, cudaStream_t st) {
     if (p.n_maps == 0) return LH_OK;
     if (p.n_maps > 0x7fffffffLL) return LH_EUNSUPPORTED;
+    auto pow2_inv = [](float s) { int e = 0; return std::frexp(s, &e) == 0.5f ? 1.0f / s : 0.0f; };
+    p.inv_stride_x = p.stride_x > 0.f ? pow2_inv(p.stride_x) : 0.f;
+    p.inv_stride_y = p.stride_y > 0.f ? pow2_inv(p.stride_y) : 0.f;
     int rc = LH_OK;
     if (vec) {
-        rc = (p.use_weight != 0) ? launch_vec<PRED, TSRC, true>(p, st) : launch_vec<PRED, TSRC, false>(p, st);
+        rc = PRED ? dispatch_pred<TSRC>(p, st) : launch_vec<false, 1, F_TOUT>(p, st);
         if (rc) return rc;
     } else {
         heatmap_scalar_kernel<PRED, TSRC><<<(unsigned)p.n_maps, kThreads, 0, st>>>(p);

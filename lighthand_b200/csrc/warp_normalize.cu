@@ -285,6 +285,8 @@ struct TileBox {       // footprint of one output tile in the source, in staged-
     int lox, hix, loy, hiy;   // clamped tap-origin range (records -2 / sw and rows -2 / sh are all-zero)
     int cx0, pitch, nrows;    // staged window: columns cx0 .. cx0+pitch-1, rows loy .. loy+nrows-1
     int flags;                // bit0 staged, bit1 need_clamp, bit2 interior
+    int gpr, total;           // groups of 4 records per staged row, groups in the window
+    unsigned inv;             // ceil(2^20 / gpr): floor(g / gpr) == (g * inv) >> 20 exactly for g < 2^10
 };
 
 // footprint too large for the staging buffer (strong down-scaling): the two tap records straight from global
@@ -319,12 +321,28 @@ __device__ __forceinline__ void warp_rows(const WarpParams& p, const TileBox& bx
     const int rec_base = -bx.loy * bx.pitch - bx.cx0;
     const float na0 = p.mean[0], na1 = p.mean[1], na2 = p.mean[2];   // NORM 1: a, b of v*a + b
     const float nb0 = p.stdv[0], nb1 = p.stdv[1], nb2 = p.stdv[2];
-    const bool bgr = p.chan_order == LH_CHAN_BGR;
+    // output pointers of this lane's column for tile row `warp`; they advance 8 rows per pass.  The BGR
+    // order (frei path) is a swap of the two outer destinations, not of the values.
+    float *d0, *d1, *d2;
+    size_t step;
+    {
+        const int oy = oy0 + warp;
+        if (p.layout == LH_LAYOUT_CHW) {
+            const size_t plane = (size_t)p.oh * p.ow;
+            d0 = p.dst + ((size_t)n * 3 * p.oh + oy) * p.ow + ox;
+            d1 = d0 + plane; d2 = d1 + plane;
+            step = (size_t)8 * p.ow;
+        } else {
+            d0 = p.dst + (((size_t)n * p.oh + oy) * p.ow + ox) * 3;
+            d1 = d0 + 1; d2 = d0 + 2;
+            step = (size_t)24 * p.ow;
+        }
+        if (p.chan_order == LH_CHAN_BGR) { float* t = d0; d0 = d2; d2 = t; }
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int r = warp + 8 * j;                 // tile row handled by this warp in pass j
-        const int oy = oy0 + r;
-        if (oy >= p.oh) break;
+        if (oy0 + r >= p.oh) break;
         const int X = (s_x0[r] + ad) >> 5, Y = (s_y0[r] + bd) >> 5;
         int ix = X >> 5, iy = Y >> 5;
         const uint32_t ax = X & 31, ay = Y & 31;
@@ -347,15 +365,8 @@ __device__ __forceinline__ void warp_rows(const WarpParams& p, const TileBox& bx
         if (NORM == 2) { o0 = s_lut[vr]; o1 = s_lut[256 + vg]; o2 = s_lut[512 + vb]; }
         else if (NORM == 1) { o0 = fmaf((float)vr, na0, nb0); o1 = fmaf((float)vg, na1, nb1); o2 = fmaf((float)vb, na2, nb2); }
         else { o0 = (float)vr; o1 = (float)vg; o2 = (float)vb; }
-        if (bgr) { const float t = o0; o0 = o2; o2 = t; }
-        if (p.layout == LH_LAYOUT_CHW) {
-            float* d = p.dst + (((size_t)n * 3) * p.oh + oy) * p.ow + ox;
-            const size_t plane = (size_t)p.oh * p.ow;
-            __stcs(d, o0); __stcs(d + plane, o1); __stcs(d + 2 * plane, o2);
-        } else {
-            float* d = p.dst + (((size_t)n * p.oh + oy) * p.ow + ox) * 3;
-            __stcs(d, o0); __stcs(d + 1, o1); __stcs(d + 2, o2);
-        }
+        __stcs(d0, o0); __stcs(d1, o1); __stcs(d2, o2);
+        d0 += step; d1 += step; d2 += step;
     }
 }
 
@@ -411,6 +422,9 @@ __global__ void __launch_bounds__(kWThreads) warp_pairs_kernel(const WarpParams 
             const bool interior = (bx.loy >= 0) & (bx.loy + bx.nrows <= p.sh) & (bx.cx0 >= 0) &
                                   (bx.cx0 + bx.pitch + 1 <= p.sw);
             bx.flags = (staged ? 1 : 0) | (need_clamp ? 2 : 0) | (interior ? 4 : 0);
+            bx.gpr = bx.pitch >> 2;
+            bx.total = bx.nrows * bx.gpr;
+            bx.inv = ((1u << 20) + bx.gpr - 1) / bx.gpr;
             s_box = bx;
         }
     }
@@ -424,9 +438,8 @@ __global__ void __launch_bounds__(kWThreads) warp_pairs_kernel(const WarpParams 
 
     // ---- phase 2: stage the footprint as position records ---------------------------------------------
     if (staged) {
-        const int gpr = bx.pitch >> 2;                  // groups of 4 records per row
-        const int total = bx.nrows * gpr;               // < 1024
-        const unsigned inv = ((1u << 20) + gpr - 1) / gpr;   // exact floor(g / gpr) for g < 2^10
+        const int gpr = bx.gpr, total = bx.total;       // total < 1024
+        const unsigned inv = bx.inv;
         if (bx.flags & 4) {
             // interior tile: every staged byte lies inside the image, no predicates, no masks
             const uint8_t* org = img + (long long)bx.loy * p.pitch + 3 * bx.cx0;
