@@ -23,7 +23,8 @@
 
 namespace lh {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 256;      // scalar kernel
+constexpr int kVecThreads = 128;   // vector kernel: 4 warps per map, 8 CTAs per SM
 constexpr int kMaxTable = 31 * 31;
 
 struct HeatmapParams {
@@ -209,13 +210,14 @@ __device__ __forceinline__ void map_tail(const HeatmapParams& p, long long m, co
 // Every CTA leaves one slot (its maps' sums, accumulated in map order); the last CTA to finish adds the
 // slots in index order -- deterministic for a given grid -- and folds the batch's PCK / EPE counts into
 // the running accumulators.
-template <bool DO_LOSS>
+template <bool DO_LOSS, int NT>
 __device__ __forceinline__ void final_reduce(const HeatmapParams& p, bool do_metric, double* s_a, double* s_b,
                                              unsigned int* s_c, int tid) {
     const int lane = tid & 31, warp = tid >> 5;
     double s = 0.0, es = 0.0;
     unsigned int wrong = 0;
-    for (unsigned int i = tid; i < gridDim.x; i += kThreads) {   // <= 3 rounds: the grid is at most SMs x 4 CTAs
+#pragma unroll 4
+    for (unsigned int i = tid; i < gridDim.x; i += NT) {   // a few rounds: the grid is at most SMs x 8 CTAs
         if (DO_LOSS) s += __ldcg(p.cta_loss + i);
         if (do_metric) { wrong += __ldcg(p.cta_wrong + i); es += __ldcg(p.cta_epe + i); }
     }
@@ -228,7 +230,7 @@ __device__ __forceinline__ void final_reduce(const HeatmapParams& p, bool do_met
         double tot = 0.0, etot = 0.0;
         unsigned int wtot = 0;
 #pragma unroll
-        for (int w = 0; w < kThreads / kWarp; ++w) { tot += s_a[w]; etot += s_b[w]; wtot += s_c[w]; }
+        for (int w = 0; w < NT / kWarp; ++w) { tot += s_a[w]; etot += s_b[w]; wtot += s_c[w]; }
         if (DO_LOSS) {
             const double loss = tot * p.loss_scale;
             if (p.loss_f64) *p.loss_f64 = loss;
@@ -308,21 +310,22 @@ struct VecBody {
 };
 
 template <bool PRED, int TSRC, int FLAGS>
-__global__ void __launch_bounds__(kThreads, TSRC == 2 ? 2 : 4) heatmap_vec_kernel(const HeatmapParams p) {
+__global__ void __launch_bounds__(kVecThreads, TSRC == 2 ? 4 : 8) heatmap_vec_kernel(const HeatmapParams p) {
     using Body = VecBody<PRED, TSRC, FLAGS>;
     constexpr bool GRAD = Body::GRAD, TOUT = Body::TOUT, DEC = Body::DEC, WGT = Body::WGT, LOSS = Body::LOSS;
     __shared__ float s_tab[TSRC == 1 ? kMaxTable : 1];
-    __shared__ double s_sum[2][kThreads / kWarp];
-    __shared__ __align__(16) float s_max[2][kThreads / kWarp];
-    __shared__ __align__(16) int s_idx[2][kThreads / kWarp];
-    __shared__ double s_fin[kThreads / kWarp];
-    __shared__ unsigned int s_finc[kThreads / kWarp];
+    __shared__ double s_sum[2][kVecThreads / kWarp];
+    __shared__ __align__(16) float s_max[2][kVecThreads / kWarp];
+    __shared__ __align__(16) int s_idx[2][kVecThreads / kWarp];
+    static_assert(kVecThreads / kWarp == 4, "the float4 / int4 reads of s_max / s_idx assume 4 warps");
+    __shared__ double s_fin[kVecThreads / kWarp];
+    __shared__ unsigned int s_finc[kVecThreads / kWarp];
     __shared__ int s_last;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     if (TSRC == 1) {
-        for (int i = tid; i < p.side * p.side; i += kThreads) s_tab[i] = p.table[i];
+        for (int i = tid; i < p.side * p.side; i += kVecThreads) s_tab[i] = p.table[i];
         __syncthreads();
     }
     const bool do_metric = DEC && p.metric_counts != nullptr;
@@ -330,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, TSRC == 2 ? 2 : 4) heatmap_vec_kerne
     constexpr int U = 4;
     const int W = p.W, H = p.H, side = p.side;
     const int vw = W >> 2;                   // vectors per row (<= 256, checked by the launcher)
-    const int rp = kThreads / vw;            // rows per pass
+    const int rp = kVecThreads / vw;            // rows per pass
     const int r0 = tid / vw, c = tid - r0 * vw;
     const int x = 4 * c;
     const bool active = r0 < rp;
@@ -363,17 +366,14 @@ __global__ void __launch_bounds__(kThreads, TSRC == 2 ? 2 : 4) heatmap_vec_kerne
     {                                                                                           \
         if (LOSS && lane == 0) {                                                                \
             double sacc = 0.0;                                                                  \
-            _Pragma("unroll") for (int w = 0; w < kThreads / kWarp; ++w) sacc += s_sum[PPAR][w]; \
+            _Pragma("unroll") for (int w = 0; w < kVecThreads / kWarp; ++w) sacc += s_sum[PPAR][w]; \
             s_cta[0] += sacc;                                                                   \
         }                                                                                       \
         if (DEC) {                                                                              \
             const float4 ma = *reinterpret_cast<const float4*>(&s_max[PPAR][0]);                \
-            const float4 mb = *reinterpret_cast<const float4*>(&s_max[PPAR][4]);                \
-            const float Mp = max_nan(max_nan(max_nan(ma.x, ma.y), max_nan(ma.z, ma.w)),         \
-                                     max_nan(max_nan(mb.x, mb.y), max_nan(mb.z, mb.w)));        \
+            const float Mp = max_nan(max_nan(ma.x, ma.y), max_nan(ma.z, ma.w));                 \
             const int4 ia = *reinterpret_cast<const int4*>(&s_idx[PPAR][0]);                    \
-            const int4 ib = *reinterpret_cast<const int4*>(&s_idx[PPAR][4]);                    \
-            int bi = min(min(min(ia.x, ia.y), min(ia.z, ia.w)), min(min(ib.x, ib.y), min(ib.z, ib.w))); \
+            int bi = min(min(ia.x, ia.y), min(ia.z, ia.w));                                     \
             if (bi == 0x7fffffff) bi = 0; /* HW == 0 only */                                    \
             float2 pgj = make_float2(0.f, 0.f), pjl = pgj, pjfirst = pgj;                       \
             if (do_metric) {                                                                    \
@@ -461,9 +461,7 @@ __global__ void __launch_bounds__(kThreads, TSRC == 2 ? 2 : 4) heatmap_vec_kerne
             if (warp == 0 && pm >= 0) LH_FINISH_PREV(pm, par ^ 1)
             if (DEC) {
                 const float4 ma = *reinterpret_cast<const float4*>(&s_max[par][0]);
-                const float4 mb = *reinterpret_cast<const float4*>(&s_max[par][4]);
-                const float M = max_nan(max_nan(max_nan(ma.x, ma.y), max_nan(ma.z, ma.w)),
-                                        max_nan(max_nan(mb.x, mb.y), max_nan(mb.z, mb.w)));
+                const float M = max_nan(max_nan(ma.x, ma.y), max_nan(ma.z, ma.w));
                 const bool mnan = M != M;
                 int cand = 0x7fffffff;
                 // threads whose own maximum IS the map maximum look up its first position inside their vector
@@ -497,7 +495,7 @@ __global__ void __launch_bounds__(kThreads, TSRC == 2 ? 2 : 4) heatmap_vec_kerne
         __syncthreads();
         if (s_last) {
             __threadfence();
-            final_reduce<LOSS>(p, do_metric, s_sum[0], s_fin, s_finc, tid);
+            final_reduce<LOSS, kVecThreads>(p, do_metric, s_sum[0], s_fin, s_finc, tid);
         }
     }
 }
@@ -617,8 +615,8 @@ __global__ void __launch_bounds__(kThreads) heatmap_scalar_kernel(const HeatmapP
         __syncthreads();
         if (s_last) {
             __threadfence();
-            if (do_loss) final_reduce<true>(p, do_metric, s_sum, s_fin, s_finc, tid);
-            else final_reduce<false>(p, do_metric, s_sum, s_fin, s_finc, tid);
+            if (do_loss) final_reduce<true, kThreads>(p, do_metric, s_sum, s_fin, s_finc, tid);
+            else final_reduce<false, kThreads>(p, do_metric, s_sum, s_fin, s_finc, tid);
         }
     }
 }
@@ -630,7 +628,7 @@ static int persistent_grid(K kernel, int* cache) {
     int dev = 0, sms = 0, occ = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 0) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kVecThreads, 0) != cudaSuccess) return 0;
     if (occ < 1) occ = 1;
     *cache = sms * occ;
     return *cache;
@@ -642,7 +640,7 @@ static int launch_vec(const HeatmapParams& p, cudaStream_t st) {
     const int cap = persistent_grid(heatmap_vec_kernel<PRED, TSRC, FLAGS>, &cache);
     if (cap <= 0) return (int)cudaGetLastError();
     const unsigned grid = (unsigned)(p.n_maps < (long long)cap ? p.n_maps : (long long)cap);
-    heatmap_vec_kernel<PRED, TSRC, FLAGS><<<grid, kThreads, 0, st>>>(p);
+    heatmap_vec_kernel<PRED, TSRC, FLAGS><<<grid, kVecThreads, 0, st>>>(p);
     return LH_OK;
 }
 
@@ -690,7 +688,7 @@ static int launch(HeatmapParams& p, bool vec, cudaStream_t st) {
 }
 
 static bool can_vec(const HeatmapParams& p) {
-    if ((p.W & 3) != 0 || (p.W >> 2) > kThreads) return false;
+    if ((p.W & 3) != 0 || (p.W >> 2) > kVecThreads) return false;
     const void* ptrs[] = {p.pred, p.target_in, p.target_out, p.grad};
     for (const void* q : ptrs) if (q && !aligned16(q)) return false;
     return true;

@@ -1,0 +1,83 @@
+#!/usr/bin/env python
+"""Developer micro-benchmark: per-op device timings (CUDA events, ring of cold buffers) to see how far
+each kernel variant is from the HBM copy roofline.  Not part of bench.py's contract."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from lighthand_b200 import ops  # noqa: E402
+
+
+def timeit(fn, ring, iters=30, warm=2):
+    """Median device time of one call, us.  The ring of calls is captured into a CUDA graph so the host-side
+    wrapper cost (tens of us in Python) cannot hide in the measurement."""
+    for i in range(ring):
+        fn(i)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(ring):
+            fn(i)
+    for _ in range(warm):
+        g.replay()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in ev:
+        a.record()
+        g.replay()
+        b.record()
+    torch.cuda.synchronize()
+    t = sorted(a.elapsed_time(b) for a, b in ev)
+    return t[len(t) // 2] * 1e3 / ring
+
+
+def main():
+    N, J, H, S, R = 256, 21, 64, 256, 4
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(0)
+    joints = [torch.rand((N, J, 2), device=dev, generator=g) * S for _ in range(R)]
+    pred = [torch.randn((N, J, H, H), device=dev, generator=g) for _ in range(R)]
+    tgt = [ops.gen_targets(j, want_weight=False)[0] for j in joints]
+    imgs = [torch.randint(0, 256, (N, S, S, 3), device=dev, dtype=torch.uint8, generator=g) for _ in range(R)]
+    th = torch.rand(N, device=dev, generator=g) * 1.5 - 0.75
+    sc = 0.8 * (1 + 0.25 * (torch.rand(N, device=dev, generator=g) * 2 - 1))
+    M = torch.zeros((N, 2, 3), dtype=torch.float64, device=dev)
+    c, s_ = torch.cos(th).double() / sc.double(), torch.sin(th).double() / sc.double()
+    M[:, 0, 0], M[:, 0, 1], M[:, 1, 0], M[:, 1, 1] = c, -s_, s_, c
+    ctr = S / 2
+    M[:, 0, 2] = ctr - (M[:, 0, 0] * ctr + M[:, 0, 1] * ctr)
+    M[:, 1, 2] = ctr - (M[:, 1, 0] * ctr + M[:, 1, 1] * ctr)
+    eye = torch.tensor([[1.0, 0, 0], [0, 1.0, 0]], dtype=torch.float64, device=dev).repeat(N, 1, 1)
+    out_img = torch.empty((N, 3, S, S), device=dev)
+    bufs = {"grad": torch.empty_like(pred[0]), "target": torch.empty_like(pred[0])}
+    hm_bytes = N * J * H * H * 4
+    k1_bytes = N * S * S * 15
+    copy_dst = torch.empty_like(pred[0])
+    res = {}
+
+    def rec(name, us, nbytes):
+        res[name] = {"us": round(us, 2), "GBps": round(nbytes / us / 1e3, 1)}
+
+    rec("torch_copy_88MB", timeit(lambda i: copy_dst.copy_(pred[i]), R), 2 * hm_bytes)
+    rec("decode_only(read)", timeit(lambda i: ops.decode(pred[i], 4.0), R), hm_bytes)
+    rec("gen_targets(write)", timeit(lambda i: ops.gen_targets(joints[i], want_weight=False, out=bufs["target"]), R), hm_bytes)
+    rec("fused loss+grad+decode", timeit(lambda i: ops.heatmap_fused(pred[i], joints[i], buffers=dict(bufs)), R), 2 * hm_bytes)
+    rec("fused loss+decode (no grad)", timeit(lambda i: ops.heatmap_fused(pred[i], joints[i], want_grad=False, buffers=dict(bufs)), R), hm_bytes)
+    rec("fused loss+grad (no decode)", timeit(lambda i: ops.heatmap_fused(pred[i], joints[i], want_decode=False, buffers=dict(bufs)), R), 2 * hm_bytes)
+    rec("fused +target", timeit(lambda i: ops.heatmap_fused(pred[i], joints[i], want_target=True, buffers=dict(bufs)), R), 3 * hm_bytes)
+    rec("jmse (target_in)", timeit(lambda i: ops.jmse_loss(pred[i], tgt[i]), R), 3 * hm_bytes)
+    for name, mat in (("warp rot+scale", M), ("warp identity", eye)):
+        rec(name + " fma", timeit(lambda i: ops.warp_normalize(imgs[i], mat, (S, S), out=out_img, exact_norm=False), R), k1_bytes)
+    lut = ops.build_norm_lut(device=dev)
+    rec("warp rot+scale lut", timeit(lambda i: ops.warp_normalize(imgs[i], M, (S, S), out=out_img, lut=lut), R), k1_bytes)
+    rec("resize torch-mode", timeit(lambda i: ops.warp_normalize(imgs[i], None, (S, S), out=out_img, interp=ops.LH_INTERP_TORCH), R), k1_bytes)
+    big_src = torch.empty((N, 3, S, S), device=dev)
+    rec("torch_copy_201MB", timeit(lambda i: out_img.copy_(big_src), 1), 2 * N * 3 * S * S * 4)
+    print(json.dumps(res, indent=1))
+
+
+if __name__ == "__main__":
+    main()
