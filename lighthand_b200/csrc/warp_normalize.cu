@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(kWThreads) warp_cv2_kernel(const WarpParams p)
 //   X' = 32(sw-1) - X  in the 1/32-px fixed-point domain  <=>  X0' = 1024(sw-1) + 31 - X0, adelta' = -adelta.
 // Normalisation: NORM 0 none (0..255), 1 single FMA v*a+b, 2 exact table (torch's three roundings).
 // ------------------------------------------------------------------------------------------------
-constexpr int kMaxPos = 3072;  // 24 KB of position records per CTA
+constexpr int kMaxPos = 5632;  // 44 KB of position records per CTA (32x64 tile, 45 degrees, unit scale)
 
 __device__ __forceinline__ int clamp_i(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
@@ -314,36 +314,42 @@ __device__ __forceinline__ int row_term(double m, double b, int y) {
     return clamp_i(sat_i32(__dmul_rn(__dadd_rn(__dmul_rn(m, (double)y), b), 1024.0)), -(1 << 30), 1 << 30) + 16;
 }
 
+constexpr int kTileW = 32;          // output tile of the fast kernel: 32 columns (lane = column) ...
+constexpr int kTileH = 64;          // ... x 64 rows (warp w renders rows 8w .. 8w+7)
+constexpr int kRowsPerWarp = kTileH / (kWThreads / 32);
+
 template <int NORM, bool CLAMP, bool STAGED>
 __device__ __forceinline__ void warp_rows(const WarpParams& p, const TileBox& bx, const uint2* s_rec, const float* s_lut,
                                           const int* s_x0, const int* s_y0, const uint8_t* img, int ad, int bd,
                                           int n, int ox, int oy0, int warp) {
+    static_assert(kRowsPerWarp == 8, "row terms are fetched as two int4 per table");
     const int rec_base = -bx.loy * bx.pitch - bx.cx0;
     const float na0 = p.mean[0], na1 = p.mean[1], na2 = p.mean[2];   // NORM 1: a, b of v*a + b
     const float nb0 = p.stdv[0], nb1 = p.stdv[1], nb2 = p.stdv[2];
-    // output pointers of this lane's column for tile row `warp`; they advance 8 rows per pass.  The BGR
-    // order (frei path) is a swap of the two outer destinations, not of the values.
-    float *d0, *d1, *d2;
-    size_t step;
-    {
-        const int oy = oy0 + warp;
-        if (p.layout == LH_LAYOUT_CHW) {
-            const size_t plane = (size_t)p.oh * p.ow;
-            d0 = p.dst + ((size_t)n * 3 * p.oh + oy) * p.ow + ox;
-            d1 = d0 + plane; d2 = d1 + plane;
-            step = (size_t)8 * p.ow;
-        } else {
-            d0 = p.dst + (((size_t)n * p.oh + oy) * p.ow + ox) * 3;
-            d1 = d0 + 1; d2 = d0 + 2;
-            step = (size_t)24 * p.ow;
-        }
-        if (p.chan_order == LH_CHAN_BGR) { float* t = d0; d0 = d2; d2 = t; }
+    const int r0 = warp * kRowsPerWarp;
+    // 32-bit element indices of this lane's column in the first row of the warp (the launcher keeps one launch
+    // below 2^31 output elements); the BGR order (frei path) swaps the two outer destinations, not the values
+    unsigned i0, i1, i2, step;
+    if (p.layout == LH_LAYOUT_CHW) {
+        const unsigned plane = (unsigned)(p.oh * p.ow);
+        i0 = ((unsigned)(n * 3) * p.oh + (oy0 + r0)) * p.ow + ox;
+        i1 = i0 + plane; i2 = i1 + plane;
+        step = (unsigned)p.ow;
+    } else {
+        i0 = (((unsigned)n * p.oh + (oy0 + r0)) * p.ow + ox) * 3u;
+        i1 = i0 + 1; i2 = i0 + 2;
+        step = 3u * (unsigned)p.ow;
     }
+    if (p.chan_order == LH_CHAN_BGR) { const unsigned t = i0; i0 = i2; i2 = t; }
+    const int4 xa = *reinterpret_cast<const int4*>(s_x0 + r0), xb = *reinterpret_cast<const int4*>(s_x0 + r0 + 4);
+    const int4 ya = *reinterpret_cast<const int4*>(s_y0 + r0), yb = *reinterpret_cast<const int4*>(s_y0 + r0 + 4);
+    const int x0v[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+    const int y0v[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+    const int rows = min(kRowsPerWarp, p.oh - (oy0 + r0));
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int r = warp + 8 * j;                 // tile row handled by this warp in pass j
-        if (oy0 + r >= p.oh) break;
-        const int X = (s_x0[r] + ad) >> 5, Y = (s_y0[r] + bd) >> 5;
+    for (int j = 0; j < kRowsPerWarp; ++j) {
+        if (j >= rows) break;
+        const int X = (x0v[j] + ad) >> 5, Y = (y0v[j] + bd) >> 5;
         int ix = X >> 5, iy = Y >> 5;
         const uint32_t ax = X & 31, ay = Y & 31;
         uint2 t0, t1;
@@ -365,8 +371,8 @@ __device__ __forceinline__ void warp_rows(const WarpParams& p, const TileBox& bx
         if (NORM == 2) { o0 = s_lut[vr]; o1 = s_lut[256 + vg]; o2 = s_lut[512 + vb]; }
         else if (NORM == 1) { o0 = fmaf((float)vr, na0, nb0); o1 = fmaf((float)vg, na1, nb1); o2 = fmaf((float)vb, na2, nb2); }
         else { o0 = (float)vr; o1 = (float)vg; o2 = (float)vb; }
-        __stcs(d0, o0); __stcs(d1, o1); __stcs(d2, o2);
-        d0 += step; d1 += step; d2 += step;
+        __stcs(p.dst + i0, o0); __stcs(p.dst + i1, o1); __stcs(p.dst + i2, o2);
+        i0 += step; i1 += step; i2 += step;
     }
 }
 
@@ -374,18 +380,19 @@ template <int NORM>
 __global__ void __launch_bounds__(kWThreads) warp_pairs_kernel(const WarpParams p) {
     __shared__ __align__(16) uint2 s_rec[kMaxPos];
     __shared__ float s_lut[NORM == 2 ? 768 : 1];
-    __shared__ int s_ad[kTile], s_bd[kTile], s_x0[kTile], s_y0[kTile];
+    __shared__ int s_ad[kTileW], s_bd[kTileW];
+    __shared__ __align__(16) int s_x0[kTileH], s_y0[kTileH];
     __shared__ TileBox s_box;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int n = blockIdx.z;
-    const int tx0 = blockIdx.x * kTile, ty0 = blockIdx.y * kTile;
+    const int tx0 = blockIdx.x * kTileW, ty0 = blockIdx.y * kTileH;
     const uint8_t* img = p.src + (long long)n * p.img_stride;
 
-    // ---- phase 1: coordinate tables (warps 0,1) and tile footprint (warp 2, lane 0); every participating
-    // thread inverts the 2x3 matrix itself (a handful of FP64 ops) so there is a single barrier
-    if (warp < 3 && (warp < 2 || lane == 0)) {
+    // ---- phase 1: column terms (warp 0), row terms (warps 1,2), tile footprint (warp 3, lane 0); every
+    // participating thread inverts the 2x3 matrix itself (a handful of FP64 ops) so there is a single barrier
+    if (warp < 4 && (warp < 3 || lane == 0)) {
         const bool flip = p.flip ? (p.flip[n] != 0) : false;
         double im[6];
         invert_affine(p.M + (long long)n * 6, im);
@@ -394,13 +401,14 @@ __global__ void __launch_bounds__(kWThreads) warp_pairs_kernel(const WarpParams 
             const int a = col_term(im[0], tx0 + lane);
             s_ad[lane] = flip ? -a : a;
             s_bd[lane] = col_term(im[3], tx0 + lane);
-        } else if (warp == 1) {
-            const int x0 = row_term(im[1], im[2], ty0 + lane);
-            s_x0[lane] = flip ? mirror - x0 : x0;
-            s_y0[lane] = row_term(im[4], im[5], ty0 + lane);
+        } else if (warp < 3) {
+            const int r = (warp - 1) * 32 + lane;
+            const int x0 = row_term(im[1], im[2], ty0 + r);
+            s_x0[r] = flip ? mirror - x0 : x0;
+            s_y0[r] = row_term(im[4], im[5], ty0 + r);
         } else {
             // the maps are monotone in x and in y, so the footprint is spanned by the 4 tile corners
-            const int cl = min(kTile, p.ow - tx0) - 1, rl = min(kTile, p.oh - ty0) - 1;
+            const int cl = min(kTileW, p.ow - tx0) - 1, rl = min(kTileH, p.oh - ty0) - 1;
             int a0 = col_term(im[0], tx0), a1 = col_term(im[0], tx0 + cl);
             if (flip) { a0 = -a0; a1 = -a1; }
             const int b0 = col_term(im[3], tx0), b1 = col_term(im[3], tx0 + cl);
@@ -418,7 +426,8 @@ __global__ void __launch_bounds__(kWThreads) warp_pairs_kernel(const WarpParams 
             bx.cx0 = bx.lox & ~3;                               // staged columns start at a multiple of 4 records
             bx.pitch = ((bx.hix - bx.cx0 + 1) + 3) & ~3;        // records per staged row
             bx.nrows = bx.hiy - bx.loy + 2;                     // rows loy .. hiy+1
-            const bool staged = bx.nrows * bx.pitch <= kMaxPos;
+            // pitch <= 256 keeps the reciprocal-multiply row split below exact (g * gpr < 2^20)
+            const bool staged = (bx.pitch <= 256) && (bx.nrows * bx.pitch <= kMaxPos);
             const bool interior = (bx.loy >= 0) & (bx.loy + bx.nrows <= p.sh) & (bx.cx0 >= 0) &
                                   (bx.cx0 + bx.pitch + 1 <= p.sw);
             bx.flags = (staged ? 1 : 0) | (need_clamp ? 2 : 0) | (interior ? 4 : 0);
@@ -438,11 +447,12 @@ __global__ void __launch_bounds__(kWThreads) warp_pairs_kernel(const WarpParams 
 
     // ---- phase 2: stage the footprint as position records ---------------------------------------------
     if (staged) {
-        const int gpr = bx.gpr, total = bx.total;       // total < 1024
+        const int gpr = bx.gpr, total = bx.total;       // total <= kMaxPos / 4
         const unsigned inv = bx.inv;
         if (bx.flags & 4) {
             // interior tile: every staged byte lies inside the image, no predicates, no masks
             const uint8_t* org = img + (long long)bx.loy * p.pitch + 3 * bx.cx0;
+#pragma unroll 2
             for (int g = tid; g < total; g += kWThreads) {
                 const int r = (int)((g * inv) >> 20), k = g - r * gpr;
                 const uint32_t* rp = reinterpret_cast<const uint32_t*>(org + (long long)r * p.pitch) + 3 * k;
@@ -489,9 +499,9 @@ __global__ void __launch_bounds__(kWThreads) warp_pairs_kernel(const WarpParams 
     }
     __syncthreads();
 
-    // ---- phase 3: lane = output column, warp w renders tile rows w, w+8, w+16, w+24 --------------------------
+    // ---- phase 3: lane = output column, warp w renders tile rows 8w .. 8w+7 ---------------------------------
     const int ox = tx0 + lane;
-    if (ox >= p.ow) return;     // columns right of the image edge lie outside the staged footprint
+    if (ox >= p.ow || ty0 + warp * kRowsPerWarp >= p.oh) return;   // outside the image = outside the staged footprint
     const int ad = s_ad[lane], bd = s_bd[lane];
     if (!staged)            warp_rows<NORM, false, false>(p, bx, s_rec, s_lut, s_x0, s_y0, img, ad, bd, n, ox, ty0, warp);
     else if (bx.flags & 2)  warp_rows<NORM, true, true>(p, bx, s_rec, s_lut, s_x0, s_y0, img, ad, bd, n, ox, ty0, warp);
@@ -619,13 +629,21 @@ extern "C" int lh_warp_normalize(const uint8_t* src, int64_t src_img_stride, int
         const bool stage = aligned16(src) && (src_pitch % 16 == 0) && (src_img_stride % 16 == 0);
         const bool words = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)src_pitch | (uintptr_t)src_img_stride) & 3u) == 0;
         if (interp == LH_INTERP_CV2_U8 && words) {
-            if (lut) {
-                warp_pairs_kernel<2><<<grid, block, 0, st>>>(p);
-            } else if (mean_std) {
-                fma_coeffs(p, mean_std);
-                warp_pairs_kernel<1><<<grid, block, 0, st>>>(p);
-            } else {
-                warp_pairs_kernel<0><<<grid, block, 0, st>>>(p);
+            if (!lut && mean_std) fma_coeffs(p, mean_std);
+            // one launch addresses the output with 32-bit element indices: chunk the batch below 2^31 elements
+            const long long per_img = 3LL * out_h * out_w;
+            if (per_img >= (1LL << 31)) return LH_EUNSUPPORTED;
+            const int chunk = (int)(((1LL << 31) - 1) / per_img);
+            for (int n0 = 0; n0 < N; n0 += chunk) {
+                const int nc = (N - n0 < chunk) ? N - n0 : chunk;
+                WarpParams q = p;
+                q.src = src + (long long)n0 * src_img_stride; q.M = fwd_affine + (long long)n0 * 6;
+                q.flip = flip ? flip + n0 : nullptr; q.dst = dst + (long long)n0 * per_img; q.N = nc;
+                if (lut && q.lut_per_image) q.lut = lut + (size_t)n0 * 768;
+                dim3 fgrid((out_w + kTileW - 1) / kTileW, (out_h + kTileH - 1) / kTileH, nc);
+                if (lut)           warp_pairs_kernel<2><<<fgrid, block, 0, st>>>(q);
+                else if (mean_std) warp_pairs_kernel<1><<<fgrid, block, 0, st>>>(q);
+                else               warp_pairs_kernel<0><<<fgrid, block, 0, st>>>(q);
             }
         } else if (interp == LH_INTERP_CV2_U8) {
             if (!lut && mean_std) fma_coeffs(p, mean_std);
