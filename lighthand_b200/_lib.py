@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblighthand_b200.so")
+LIB_PATH = os.environ.get("LIGHTHAND_B200_LIB") or os.path.join(_HERE, "liblighthand_b200.so")   # env override: kernel-variant experiments
 
 LH_INTERP_CV2_U8, LH_INTERP_CV2_F32, LH_INTERP_TORCH = 0, 1, 2
 LH_CHAN_RGB, LH_CHAN_BGR = 0, 1

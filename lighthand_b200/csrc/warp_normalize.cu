@@ -277,7 +277,10 @@ __global__ void __launch_bounds__(kWThreads) warp_cv2_kernel(const WarpParams p)
 //   X' = 32(sw-1) - X  in the 1/32-px fixed-point domain  <=>  X0' = 1024(sw-1) + 31 - X0, adelta' = -adelta.
 // Normalisation: NORM 0 none (0..255), 1 single FMA v*a+b, 2 exact table (torch's three roundings).
 // ------------------------------------------------------------------------------------------------
-constexpr int kMaxPos = 5632;  // 44 KB of position records per CTA (32x64 tile, 45 degrees, unit scale)
+#ifndef LH_FAST_MAXPOS
+#define LH_FAST_MAXPOS 3200
+#endif
+constexpr int kMaxPos = LH_FAST_MAXPOS;  // position records per CTA (3200 = 25 KB: a 32x32 tile rotated 45 degrees at unit scale, row pitch padded to 16)
 
 __device__ __forceinline__ int clamp_i(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
@@ -314,15 +317,22 @@ __device__ __forceinline__ int row_term(double m, double b, int y) {
     return clamp_i(sat_i32(__dmul_rn(__dadd_rn(__dmul_rn(m, (double)y), b), 1024.0)), -(1 << 30), 1 << 30) + 16;
 }
 
-constexpr int kTileW = 32;          // output tile of the fast kernel: 32 columns (lane = column) ...
-constexpr int kTileH = 64;          // ... x 64 rows (warp w renders rows 8w .. 8w+7)
-constexpr int kRowsPerWarp = kTileH / (kWThreads / 32);
+#ifndef LH_FAST_THREADS
+#define LH_FAST_THREADS 128
+#endif
+// CTA shape of the fast kernel, chosen by measurement on B200 (tools/run_variants*.sh): 128 threads on a 32x32
+// tile at 8 CTAs / SM beat 256 threads on 32x64 (4-6 CTAs / SM) by 3-5 %; a persistent, register-prefetching
+// variant (2 CTAs / SM) was 1.5-2x slower and was dropped.
+constexpr int kFThreads = LH_FAST_THREADS;   // CTA size of the fast kernel
+constexpr int kTileW = 32;                   // output tile: 32 columns (lane = column) ...
+constexpr int kRowsPerWarp = 8;              // ... x 8 rows per warp (warp w renders rows 8w .. 8w+7)
+constexpr int kTileH = kRowsPerWarp * (kFThreads / 32);
 
 template <int NORM, bool CLAMP, bool STAGED>
 __device__ __forceinline__ void warp_rows(const WarpParams& p, const TileBox& bx, const uint2* s_rec, const float* s_lut,
                                           const int* s_x0, const int* s_y0, const uint8_t* img, int ad, int bd,
                                           int n, int ox, int oy0, int warp) {
-    static_assert(kRowsPerWarp == 8, "row terms are fetched as two int4 per table");
+    
     const int rec_base = -bx.loy * bx.pitch - bx.cx0;
     const float na0 = p.mean[0], na1 = p.mean[1], na2 = p.mean[2];   // NORM 1: a, b of v*a + b
     const float nb0 = p.stdv[0], nb1 = p.stdv[1], nb2 = p.stdv[2];
@@ -376,8 +386,11 @@ __device__ __forceinline__ void warp_rows(const WarpParams& p, const TileBox& bx
     }
 }
 
+#ifndef LH_FAST_MINB
+#define LH_FAST_MINB 8
+#endif
 template <int NORM>
-__global__ void __launch_bounds__(kWThreads) warp_pairs_kernel(const WarpParams p) {
+__global__ void __launch_bounds__(kFThreads, LH_FAST_MINB) warp_pairs_kernel(const WarpParams p) {
     __shared__ __align__(16) uint2 s_rec[kMaxPos];
     __shared__ float s_lut[NORM == 2 ? 768 : 1];
     __shared__ int s_ad[kTileW], s_bd[kTileW];
@@ -390,9 +403,11 @@ __global__ void __launch_bounds__(kWThreads) warp_pairs_kernel(const WarpParams 
     const int tx0 = blockIdx.x * kTileW, ty0 = blockIdx.y * kTileH;
     const uint8_t* img = p.src + (long long)n * p.img_stride;
 
-    // ---- phase 1: column terms (warp 0), row terms (warps 1,2), tile footprint (warp 3, lane 0); every
-    // participating thread inverts the 2x3 matrix itself (a handful of FP64 ops) so there is a single barrier
-    if (warp < 4 && (warp < 3 || lane == 0)) {
+    // ---- phase 1: column terms (warp 0), row terms (next kTileH/32 warps), tile footprint (one more lane);
+    // every participating thread inverts the 2x3 matrix itself (a handful of FP64 ops): a single barrier
+    constexpr int kRowWarps = kTileH / 32;
+    static_assert(kRowWarps >= 1 && kRowWarps + 2 <= kFThreads / 32, "phase-1 roles need kRowWarps + 2 warps");
+    if (warp <= kRowWarps + 1 && (warp <= kRowWarps || lane == 0)) {
         const bool flip = p.flip ? (p.flip[n] != 0) : false;
         double im[6];
         invert_affine(p.M + (long long)n * 6, im);
@@ -401,7 +416,7 @@ __global__ void __launch_bounds__(kWThreads) warp_pairs_kernel(const WarpParams 
             const int a = col_term(im[0], tx0 + lane);
             s_ad[lane] = flip ? -a : a;
             s_bd[lane] = col_term(im[3], tx0 + lane);
-        } else if (warp < 3) {
+        } else if (warp <= kRowWarps) {
             const int r = (warp - 1) * 32 + lane;
             const int x0 = row_term(im[1], im[2], ty0 + r);
             s_x0[r] = flip ? mirror - x0 : x0;
@@ -424,7 +439,10 @@ __global__ void __launch_bounds__(kWThreads) warp_pairs_kernel(const WarpParams 
             bx.loy = clamp_i(iymin, -2, p.sh); bx.hiy = clamp_i(iymax, -2, p.sh);
             const bool need_clamp = (bx.lox != ixmin) | (bx.hix != ixmax) | (bx.loy != iymin) | (bx.hiy != iymax);
             bx.cx0 = bx.lox & ~3;                               // staged columns start at a multiple of 4 records
-            bx.pitch = ((bx.hix - bx.cx0 + 1) + 3) & ~3;        // records per staged row
+            // records per staged row, a multiple of 16 (= 128 bytes = one sweep over the 32 banks): a lane that
+            // moves to the next source row together with the next column stays on unit stride in bank space,
+            // so the LDS.64 tap loads of rotated tiles are (nearly) conflict-free
+            bx.pitch = ((bx.hix - bx.cx0 + 1) + 15) & ~15;
             bx.nrows = bx.hiy - bx.loy + 2;                     // rows loy .. hiy+1
             // pitch <= 256 keeps the reciprocal-multiply row split below exact (g * gpr < 2^20)
             const bool staged = (bx.pitch <= 256) && (bx.nrows * bx.pitch <= kMaxPos);
@@ -439,7 +457,7 @@ __global__ void __launch_bounds__(kWThreads) warp_pairs_kernel(const WarpParams 
     }
     if (NORM == 2) {
         const float* lut = p.lut + (p.lut_per_image ? (size_t)n * 768 : 0);
-        for (int i = tid; i < 768; i += kWThreads) s_lut[i] = lut[i];
+        for (int i = tid; i < 768; i += kFThreads) s_lut[i] = lut[i];
     }
     __syncthreads();
     const TileBox bx = s_box;
@@ -453,7 +471,7 @@ __global__ void __launch_bounds__(kWThreads) warp_pairs_kernel(const WarpParams 
             // interior tile: every staged byte lies inside the image, no predicates, no masks
             const uint8_t* org = img + (long long)bx.loy * p.pitch + 3 * bx.cx0;
 #pragma unroll 2
-            for (int g = tid; g < total; g += kWThreads) {
+            for (int g = tid; g < total; g += kFThreads) {
                 const int r = (int)((g * inv) >> 20), k = g - r * gpr;
                 const uint32_t* rp = reinterpret_cast<const uint32_t*>(org + (long long)r * p.pitch) + 3 * k;
                 const uint32_t w0 = __ldg(rp), w1 = __ldg(rp + 1), w2 = __ldg(rp + 2), w3 = __ldg(rp + 3);
@@ -465,7 +483,7 @@ __global__ void __launch_bounds__(kWThreads) warp_pairs_kernel(const WarpParams 
             }
         } else {
             const int rowb = 3 * p.sw;
-            for (int g = tid; g < total; g += kWThreads) {
+            for (int g = tid; g < total; g += kFThreads) {
                 const int r = (int)((g * inv) >> 20), k = g - r * gpr;
                 const int y = bx.loy + r, x = bx.cx0 + 4 * k;
                 uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
@@ -641,9 +659,9 @@ extern "C" int lh_warp_normalize(const uint8_t* src, int64_t src_img_stride, int
                 q.flip = flip ? flip + n0 : nullptr; q.dst = dst + (long long)n0 * per_img; q.N = nc;
                 if (lut && q.lut_per_image) q.lut = lut + (size_t)n0 * 768;
                 dim3 fgrid((out_w + kTileW - 1) / kTileW, (out_h + kTileH - 1) / kTileH, nc);
-                if (lut)           warp_pairs_kernel<2><<<fgrid, block, 0, st>>>(q);
-                else if (mean_std) warp_pairs_kernel<1><<<fgrid, block, 0, st>>>(q);
-                else               warp_pairs_kernel<0><<<fgrid, block, 0, st>>>(q);
+                if (lut)           warp_pairs_kernel<2><<<fgrid, kFThreads, 0, st>>>(q);
+                else if (mean_std) warp_pairs_kernel<1><<<fgrid, kFThreads, 0, st>>>(q);
+                else               warp_pairs_kernel<0><<<fgrid, kFThreads, 0, st>>>(q);
             }
         } else if (interp == LH_INTERP_CV2_U8) {
             if (!lut && mean_std) fma_coeffs(p, mean_std);
