@@ -19,6 +19,15 @@
 
 namespace lh {
 
+#ifdef LH_DEBUG_BOUNDS
+// compute-sanitizer is not available on the GPU pool: a debug build counts every shared-memory index of the
+// fast kernel that falls outside the staged window (tools/check_bounds.py reads the counter back)
+__device__ unsigned long long g_lh_oob = 0ull;
+#define LH_BOUNDS(cond) do { if (!(cond)) atomicAdd(&g_lh_oob, 1ull); } while (0)
+#else
+#define LH_BOUNDS(cond) do { } while (0)
+#endif
+
 constexpr int kTile = 32;
 constexpr int kWThreads = 256;
 constexpr int kStageBytes = 24 * 1024;
@@ -366,6 +375,8 @@ __device__ __forceinline__ void warp_rows(const WarpParams& p, const TileBox& bx
         if (STAGED) {
             if (CLAMP) { ix = clamp_i(ix, bx.lox, bx.hix); iy = clamp_i(iy, bx.loy, bx.hiy); }
             const uint2* q = s_rec + (iy * bx.pitch + ix + rec_base);
+            LH_BOUNDS(ix >= bx.cx0 && ix < bx.cx0 + bx.pitch && iy >= bx.loy && iy + 1 < bx.loy + bx.nrows &&
+                      (iy - bx.loy + 1) * bx.pitch + (ix - bx.cx0) < kMaxPos);
             t0 = q[0]; t1 = q[bx.pitch];
         } else {
             const uint4 t = taps_from_global(img, p.pitch, p.sw, p.sh, ix, iy);
@@ -476,6 +487,7 @@ __global__ void __launch_bounds__(kFThreads, LH_FAST_MINB) warp_pairs_kernel(con
                 const uint32_t* rp = reinterpret_cast<const uint32_t*>(org + (long long)r * p.pitch) + 3 * k;
                 const uint32_t w0 = __ldg(rp), w1 = __ldg(rp + 1), w2 = __ldg(rp + 2), w3 = __ldg(rp + 3);
                 uint4* d = reinterpret_cast<uint4*>(s_rec + r * bx.pitch + 4 * k);
+                LH_BOUNDS(r >= 0 && r < bx.nrows && k >= 0 && 4 * k + 3 < bx.pitch && r * bx.pitch + 4 * k + 3 < kMaxPos);
                 d[0] = make_uint4(__byte_perm(w0, w1, 0x4130), __byte_perm(w0, w1, 0x0052),
                                   __byte_perm(w0, w1, 0x7463), __byte_perm(w1, w2, 0x0041));
                 d[1] = make_uint4(__byte_perm(w1, w2, 0x6352), __byte_perm(w2, w2, 0x0030),
@@ -510,6 +522,7 @@ __global__ void __launch_bounds__(kFThreads, LH_FAST_MINB) warp_pairs_kernel(con
                     a[i] &= m; c[i] &= m;
                 }
                 uint4* d = reinterpret_cast<uint4*>(s_rec + r * bx.pitch + 4 * k);
+                LH_BOUNDS(r >= 0 && r < bx.nrows && k >= 0 && 4 * k + 3 < bx.pitch && r * bx.pitch + 4 * k + 3 < kMaxPos);
                 d[0] = make_uint4(a[0], c[0], a[1], c[1]);
                 d[1] = make_uint4(a[2], c[2], a[3], c[3]);
             }
@@ -598,6 +611,15 @@ static void fma_coeffs(WarpParams& p, const float* mean_std) {
         p.stdv[i] = (float)(-(double)mean_std[i] / sd);
     }
 }
+
+#ifdef LH_DEBUG_BOUNDS
+extern "C" unsigned long long lh_debug_oob_count(void) {
+    unsigned long long v = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&v, g_lh_oob, sizeof(v));
+    return v;
+}
+#endif
 
 extern "C" int lh_norm_lut_build(const double* chan_gain, int N, const float* mean_std, float* lut,
                                  lh_stream_t stream) {

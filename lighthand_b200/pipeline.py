@@ -196,6 +196,14 @@ class PreparedStep:
             check(rc, "prepared step")
 
 
+    def launch_split(self, stream_k1: int, stream_fused: int) -> None:
+        """K1 and the fused heat-map pass touch disjoint data (images -> input; pred/joints -> grad/coords), so
+        they may run concurrently: K1 of the next batch (data stage) overlaps the loss stage of the current one."""
+        rc = self._f1(*self._k1, stream_k1) or self._f2(self._aref, stream_fused)
+        if rc:
+            check(rc, "prepared step (split streams)")
+
+
 class HostPipeline:
     """C-ABI context (lh_pipeline_*, include/lighthand_b200.h): host numpy buffers in, host results out.
     ``submit``/``wait`` are double-buffered; ``step`` = submit + wait."""
