@@ -182,7 +182,7 @@ class PreparedStep:
 
     def launch(self, stream: Optional[int] = None, events=None) -> None:
         """Enqueue the step on ``stream`` (raw cudaStream_t; default: torch's current stream).  ``events``
-        = (e0, e1, e2) torch events recorded before K1, after K1 and after the fused kernel."""
+        = (e0, e1[, e2]) torch events recorded before K1, after K1 and (if given) after the fused kernel."""
         st = torch.cuda.current_stream().cuda_stream if stream is None else stream
         if events is not None:
             events[0].record()
@@ -190,11 +190,10 @@ class PreparedStep:
         if events is not None:
             events[1].record()
         rc = rc or self._f2(self._aref, st)
-        if events is not None:
+        if events is not None and len(events) > 2:
             events[2].record()
         if rc:
             check(rc, "prepared step")
-
 
     def launch_split(self, stream_k1: int, stream_fused: int) -> None:
         """K1 and the fused heat-map pass touch disjoint data (images -> input; pred/joints -> grad/coords), so
