@@ -206,6 +206,19 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def load_traffic(kernel_key):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (C2 only)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_final_traffic.json")) as f:
+            t = json.load(f)["kernels"]
+        for name, v in t.items():
+            if kernel_key in name:
+                return v["dram_read_bytes"] + v["dram_write_bytes"]
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
     wl = WORKLOADS[args.workload]
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -390,7 +403,10 @@ def run_ours(args):
                    "materialize_target": bool(args.materialize_target), "train": bool(train),
                    "launch": "pre-marshalled C-ABI calls, 2 kernels/step (K1; K2+K3+K4+K5 fused)", "normalise": "one FMA per value (<=2 ulp of torch)"},
         "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak,
+                     "traffic": load_traffic("warp_pairs" if dom[0] == "warp_normalize" else "heatmap_vec") if args.workload == "C2" and not args.batch else None,
+                     "traffic_note": "dram__bytes_read+write per launch, ncu --set full (profiles/r01_final_traffic.json); below the algorithmic bytes because part of the output is still dirty in the 126 MB L2 when the kernel ends",
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dom[1], "avg_launch_ms": dom[2]},
         "kernels": {"warp_normalize": {"ms": k1_ms, "GBps": k1_bytes / (k1_ms * 1e-3) / 1e9, "bytes": k1_bytes},
                     "heatmap_fused": {"ms": fused_ms, "GBps": fused_bytes / (fused_ms * 1e-3) / 1e9, "bytes": fused_bytes},
