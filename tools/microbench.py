@@ -71,15 +71,6 @@ def main():
     rec("jmse (target_in)", timeit(lambda i: ops.jmse_loss(pred[i], tgt[i]), R), 3 * hm_bytes)
     for name, mat in (("warp rot+scale", M), ("warp identity", eye)):
         rec(name + " fma", timeit(lambda i: ops.warp_normalize(imgs[i], mat, (S, S), out=out_img, exact_norm=False), R), k1_bytes)
-    # hypothesis test: source already resident in L2 when K1 starts (a cheap read pass over the 50 MB batch first)
-    iv = [im.view(-1).view(torch.int32) for im in imgs]
-    acc = torch.zeros((), dtype=torch.int64, device=dev)
-    t_pre = timeit(lambda i: torch.sum(iv[i], dim=(0,), dtype=torch.int64, out=acc), R)
-    rec("l2_prefetch_pass_only(50MB read)", t_pre, N * S * S * 3)
-    def pre_then_warp(i):
-        torch.sum(iv[i], dim=(0,), dtype=torch.int64, out=acc)
-        ops.warp_normalize(imgs[i], M, (S, S), out=out_img, exact_norm=False)
-    rec("prefetch+warp rot+scale (K1 part)", timeit(pre_then_warp, R) - t_pre, k1_bytes)
     lut = ops.build_norm_lut(device=dev)
     rec("warp rot+scale lut", timeit(lambda i: ops.warp_normalize(imgs[i], M, (S, S), out=out_img, lut=lut), R), k1_bytes)
     rec("resize torch-mode", timeit(lambda i: ops.warp_normalize(imgs[i], None, (S, S), out=out_img, interp=ops.LH_INTERP_TORCH), R), k1_bytes)
