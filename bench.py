@@ -39,6 +39,10 @@ WORKLOADS = {
                desc="C3 FreiHAND-shaped eval: batch 256/GPU, 224x224 -> 56x56 heatmaps sigma=2"),
     "C5": dict(batch=128, S=512, H=128, sigma=3, train=True,
                desc="C5 high-resolution stress: batch 128/GPU, 512x512 -> 128x128 heatmaps sigma=3"),
+    # C4 is a whole evaluation sweep (strong scaling), see run_eval_sweep
+    "C4": dict(batch=256, S=256, H=64, sigma=2, train=False, total=99792,
+               desc="C4 LightHand99K-sized eval sweep: 99,792 images batch-sharded over the ranks, 256x256 -> 64x64, "
+                    "eval pipeline + PCK curve (mm 0..30) / AUC / EPE, one metric all-reduce"),
 }
 
 
@@ -428,6 +432,117 @@ def run_ours(args):
     return 0
 
 
+def run_eval_sweep(args):
+    """BASELINE.json configs[3]: the full 99,792-image evaluation, batch-sharded across the ranks (strong
+    scaling).  Per batch: K1 warp+normalise, fused targets/loss/decode/PCK@0.2/EPE, PCK-curve histogram update;
+    at the end ONE all-reduce of the packed counters and the curve state, then AUC / EPE on the host."""
+    wl = WORKLOADS["C4"]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    import torch.distributed as dist
+    from lighthand_b200 import ops
+    from lighthand_b200.distributed import all_reduce_metrics, shard_range
+    from lighthand_b200.pipeline import HeatmapPipeline
+    from lighthand_b200.utils.argparser import CurveAccumulator
+    from lighthand_b200.utils.preprocessing import batch_patch_matrices
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, S, H, sigma, total = wl["batch"], wl["S"], wl["H"], wl["sigma"], wl["total"]
+    lo, hi = shard_range(total, rank, world)
+    n_local = hi - lo
+    full, tail = divmod(n_local, B)
+    ring = max(2, args.ring)
+    stride = S / H
+    g = torch.Generator(device=dev).manual_seed(4321 + rank)
+
+    def make_sets(pipe, nb, count):
+        out = []
+        for r_i in range(count):
+            imgs, joints, bbox, scale, rot, flip = synth_host(nb, S, seed=(4321 + rank) * 100 + r_i)
+            trans, _ = batch_patch_matrices(bbox, flip, scale, rot, (S, S), (S, S))
+            vis = (np.random.default_rng(r_i).uniform(size=(nb, 21, 1)) < 0.8).astype(np.float32)
+            d_j = torch.from_numpy(np.concatenate([joints, vis], -1)).to(dev)
+            tgt, _ = ops.gen_targets(d_j, (H, H), (stride, stride), sigma, want_weight=False)
+            d_pred = tgt + 0.1 * torch.randn(tgt.shape, device=dev, generator=g)
+            cat = torch.randint(0, 4, (nb,), device=dev, dtype=torch.int32, generator=g)
+            step = pipe.prepare(torch.from_numpy(imgs).to(dev), torch.from_numpy(np.ascontiguousarray(trans.astype(np.float64))).to(dev),
+                                d_j, d_pred, flip=torch.from_numpy(np.ascontiguousarray(flip.astype(np.uint8))).to(dev))
+            out.append((step, d_j, cat))
+        return out
+
+    pipe = HeatmapPipeline(B, (S, S), (S, S), (H, H), sigma=sigma, train=False, device=dev)
+    sets = make_sets(pipe, B, ring)
+    pipe_t = HeatmapPipeline(tail, (S, S), (S, S), (H, H), sigma=sigma, train=False, device=dev) if tail else None
+    sets_t = make_sets(pipe_t, tail, 1) if tail else []
+    acc = CurveAccumulator([0, 30], "mm", device=dev)
+
+    def sweep():
+        for i in range(full):
+            step, d_j, cat = sets[i % ring]
+            step.launch()
+            acc.update(pipe.buffers["coords"], d_j, None, cat)
+        if tail:
+            step, d_j, cat = sets_t[0]
+            step.launch()
+            acc.update(pipe_t.buffers["coords"], d_j, None, cat)
+            # fold the tail pipeline's counters into the main accumulators
+            pipe.meter.counts.add_(pipe_t.meter.counts); pipe.meter.sums.add_(pipe_t.meter.sums)
+            pipe_t.reset_metrics()
+        if world > 1:
+            all_reduce_metrics([pipe.meter.counts, pipe.meter.sums] + acc.tensors())
+
+    def reset():
+        pipe.reset_metrics()
+        for t in acc.tensors():
+            t.zero_()
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        sweep()
+    torch.cuda.synchronize()
+    reps = max(1, min(args.steps, 5))
+    times = []
+    for _ in range(reps):
+        reset()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sweep()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        times.append(ms)
+    res = acc.finalize()
+    m = pipe.meter.result()
+    if rank == 0:
+        ms = float(np.median(times))
+        line = {
+            "metric": METRIC, "value": total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": reps, "warmup": 2,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8->f32", "data": "synthetic (ring of %d resident batches per rank, reused across the sweep)" % ring,
+            "config": {"workload": wl["desc"], "global_batch": total, "batch_per_gpu": B, "images_per_rank": n_local,
+                       "parallelism": f"dp{world} (contiguous shards, one all-reduce of counters + curve histograms)"},
+            "check": {"n_images": m["n_images"], "n_wrong": m["n_wrong"], "n_total": m["n_total"], "pck@0.2": m["pck"],
+                      "epe_px": m["epe"], "mean_auc": float(res["mean_auc"][0]), "mean_epe_mm": float(res["mean_auc"][1]),
+                      "curve_count_at_T50": int(acc.hist.sum(0)[:50].sum().item())},
+            "gpu_launches": 3 * (full + (1 if tail else 0)),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -452,6 +567,8 @@ def main():
         return subprocess.call(cmd)
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.workload == "C4":
+        return run_eval_sweep(args)
     return run_ours(args)
 
 
