@@ -99,6 +99,51 @@ class CurveAccumulator:
         return out
 
 
+def pred_store(args, dataloader, model, pbar):
+    """src/utils/argparser.py:246-281: run the model over the evaluation loader, decode (x4), bucket by pose
+    category and write ``output/<args.name>/evaluation.json`` in the reference's schema
+    ``[{category: {"bb": [n], "pred": [n][21][2], "gt": [n][21][3]}}]``.
+
+    The decode and the bounding-box diagonals are computed on the device (``ops.decode``; float32
+    max/min/sqrt like the reference's per-sample loop); one device->host copy per batch feeds the JSON lists.
+    Returns the meta dict as well."""
+    from .dir import dump
+    meta = {name: {"bb": [], "pred": [], "gt": []} for name in POSE_CATEGORIES}
+    dev = next(model.parameters()).device
+    with torch.no_grad():
+        for images, gt_2d_joints, annos in dataloader:
+            anno, _idx = annos
+            pred = model(images.to(dev, non_blocking=True))
+            coords, _mv, _ai = ops.decode(pred.float().contiguous(), 4.0)
+            gt = gt_2d_joints.to(dev, torch.float32)
+            width = gt[:, :, 0].amax(1) - gt[:, :, 0].amin(1)
+            height = gt[:, :, 1].amax(1) - gt[:, :, 1].amin(1)
+            bbox = torch.sqrt(width * width + height * height)
+            pred_l, bbox_l, gt_l = coords.cpu().tolist(), bbox.cpu().tolist(), gt_2d_joints.tolist()
+            for i, name in enumerate(anno):
+                meta[name]["bb"].append(bbox_l[i])
+                meta[name]["pred"].append(pred_l[i])
+                meta[name]["gt"].append(gt_l[i])
+            pbar.update(1)
+    os.makedirs(os.path.join("output", args.name), exist_ok=True)
+    dump(os.path.join("output", args.name, "evaluation.json"), meta)
+    return meta
+
+
+def write_pck_eval(file_name, pck_list):
+    """The ``pck_eval_*.txt`` writer of src/tools/wearable_eval_2d.py:64-79: one line per (category, model):
+    ``category;model;auc;epe;pck_0;...;pck_99;``.  ``pck_list`` = [[pred_eval result, model name], ...]."""
+    with open(file_name, "w") as f:
+        for total_pck, name in pck_list:
+            for p_type in total_pck:
+                f.write("{};{};{:.2f};{:.2f};".format(p_type, name, total_pck[p_type][0], total_pck[p_type][1]))
+                n = len(total_pck[p_type][2])
+                for idx, pck in enumerate(total_pck[p_type][2]):
+                    f.write("{:.2f};".format(pck))
+                    if idx == n - 1:
+                        f.write("\n")
+
+
 def pred_eval_meta(meta, T_list, method):
     """pred_eval on an in-memory meta dict {category: {"bb", "pred", "gt"}} (what pred_store dumps)."""
     names = list(meta.keys())

@@ -71,6 +71,8 @@ def main():
     rec("jmse (target_in)", timeit(lambda i: ops.jmse_loss(pred[i], tgt[i]), R), 3 * hm_bytes)
     for name, mat in (("warp rot+scale", M), ("warp identity", eye)):
         rec(name + " fma", timeit(lambda i: ops.warp_normalize(imgs[i], mat, (S, S), out=out_img, exact_norm=False), R), k1_bytes)
+    const_imgs = [torch.full_like(imgs[0], 128) for _ in range(R)]
+    rec("warp rot+scale fma, CONSTANT source", timeit(lambda i: ops.warp_normalize(const_imgs[i], M, (S, S), out=out_img, exact_norm=False), R), k1_bytes)
     lut = ops.build_norm_lut(device=dev)
     rec("warp rot+scale lut", timeit(lambda i: ops.warp_normalize(imgs[i], M, (S, S), out=out_img, lut=lut), R), k1_bytes)
     rec("resize torch-mode", timeit(lambda i: ops.warp_normalize(imgs[i], None, (S, S), out=out_img, interp=ops.LH_INTERP_TORCH), R), k1_bytes)
