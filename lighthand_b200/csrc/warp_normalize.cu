@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(kWThreads) warp_cv2_kernel(const WarpParams p)
 #ifndef LH_FAST_MAXPOS
 #define LH_FAST_MAXPOS 3200
 #endif
-constexpr int kMaxPos = LH_FAST_MAXPOS;  // position records per CTA (3200 = 25 KB: a 32x32 tile rotated 45 degrees at unit scale, row pitch padded to 16)
+constexpr int kMaxPos = LH_FAST_MAXPOS;  // position records per CTA (3200 = 25 KB: a 32x32 tile rotated 45 degrees at unit scale is 62 x 49)
 
 __device__ __forceinline__ int clamp_i(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
@@ -450,17 +450,18 @@ __global__ void __launch_bounds__(kFThreads, LH_FAST_MINB) warp_pairs_kernel(con
             bx.loy = clamp_i(iymin, -2, p.sh); bx.hiy = clamp_i(iymax, -2, p.sh);
             const bool need_clamp = (bx.lox != ixmin) | (bx.hix != ixmax) | (bx.loy != iymin) | (bx.hiy != iymax);
             bx.cx0 = bx.lox & ~3;                               // staged columns start at a multiple of 4 records
-            // records per staged row, a multiple of 16 (= 128 bytes = one sweep over the 32 banks): a lane that
-            // moves to the next source row together with the next column stays on unit stride in bank space,
-            // so the LDS.64 tap loads of rotated tiles are (nearly) conflict-free
-            bx.pitch = ((bx.hix - bx.cx0 + 1) + 15) & ~15;
+            // records per staged row: a multiple of 8 plus 6 (rows stay 16-byte aligned for the STS.128 of the
+            // staging pass).  Measured with ncu on the benchmark's rotation mix: the +6 skew between rows cuts the
+            // bank conflicts of the LDS.64 tap loads by ~30 % and those of the staging stores by ~20 % against a
+            // 128-byte-multiple pitch (profiles/r01 notes in DESIGN.md)
+            bx.pitch = (((bx.hix - bx.cx0 + 1) + 7) & ~7) + 6;
             bx.nrows = bx.hiy - bx.loy + 2;                     // rows loy .. hiy+1
             // pitch <= 256 keeps the reciprocal-multiply row split below exact (g * gpr < 2^20)
             const bool staged = (bx.pitch <= 256) && (bx.nrows * bx.pitch <= kMaxPos);
+            bx.gpr = ((bx.hix - bx.cx0 + 1) + 3) >> 2;          // only the columns that can be touched are staged
             const bool interior = (bx.loy >= 0) & (bx.loy + bx.nrows <= p.sh) & (bx.cx0 >= 0) &
-                                  (bx.cx0 + bx.pitch + 1 <= p.sw);
+                                  (bx.cx0 + 4 * bx.gpr + 1 <= p.sw);
             bx.flags = (staged ? 1 : 0) | (need_clamp ? 2 : 0) | (interior ? 4 : 0);
-            bx.gpr = bx.pitch >> 2;
             bx.total = bx.nrows * bx.gpr;
             bx.inv = ((1u << 20) + bx.gpr - 1) / bx.gpr;
             s_box = bx;
