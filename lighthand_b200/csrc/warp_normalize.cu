@@ -585,6 +585,128 @@ __global__ void __launch_bounds__(kWThreads) resize_torch_kernel(const WarpParam
     store_tile(p, out, n, oy, ox);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fast resize path (LH_INTERP_TORCH without flip / gain, 4-byte aligned rows): same structure as
+// warp_pairs_kernel -- the source window of a 32x32 output tile is staged once as pair records
+// {R[x] R[x+1] G[x] G[x+1] | B[x] B[x+1]} (right edge clamped, like torch's min(x0+1, in-1)), lane = output
+// column, a warp renders 8 rows; per pixel two LDS.64, byte->float conversions and 7 float ops per channel.
+// The interpolation weights are torch's (area_pixel_compute_source_index, align_corners=False); the value is
+// computed in byte units and scaled once, v*a + b with a = 1/(255 std), b = -mean/std: within ~3 ulp of the
+// exact-order kernel below (which stays the path for flip / gain / unaligned rows) and far inside the 1e-5
+// tolerance of this mode.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRMaxPos = 2304;   // 18 KB: up to 48 x 48 source records per 32x32 output tile (scale <= 1.4)
+
+__global__ void __launch_bounds__(kFThreads, 8) resize_pairs_kernel(const WarpParams p) {
+    static_assert(kFThreads == 128 && kTileH == 32 && kRowsPerWarp == 8, "tile roles below assume 4 warps x 8 rows");
+    __shared__ __align__(16) uint2 s_rec[kRMaxPos];
+    __shared__ int s_cx[kTileW];                       // record column of each output column (window-relative)
+    __shared__ float s_lx[kTileW];                     // lambda_1 of each output column
+    __shared__ __align__(16) int s_r0[kTileH], s_r1[kTileH];   // record rows (window-relative) of each output row
+    __shared__ __align__(16) float s_ly[kTileH];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int n = blockIdx.z;
+    const int tx0 = blockIdx.x * kTileW, ty0 = blockIdx.y * kTileH;
+    const uint8_t* img = p.src + (long long)n * p.img_stride;
+
+    // torch: scale = in / out (float32); src = max(0, scale * (dst + 0.5) - 0.5); i0 = (int)src; lambda1 = src - i0
+    const float sy = __fdiv_rn((float)p.sh, (float)p.oh), sx = __fdiv_rn((float)p.sw, (float)p.ow);
+    auto src_index = [](float scale, int d) {
+        const float f = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)d, 0.5f)), 0.5f);
+        return f < 0.f ? 0.f : f;
+    };
+    const int cl = min(kTileW, p.ow - tx0) - 1, rl = min(kTileH, p.oh - ty0) - 1;
+    const int x_lo = min((int)src_index(sx, tx0), p.sw - 1) & ~3;              // staged columns start at a multiple of 4
+    const int x_hi = min((int)src_index(sx, tx0 + cl), p.sw - 1);
+    const int y_lo = min((int)src_index(sy, ty0), p.sh - 1);
+    const int y_hi = min(min((int)src_index(sy, ty0 + rl), p.sh - 1) + 1, p.sh - 1);
+    const int gpr = (x_hi - x_lo + 4) >> 2, pitch = ((4 * gpr + 7) & ~7) + 6, nrows = y_hi - y_lo + 1;
+    if (warp == 0) {
+        const float f = src_index(sx, tx0 + min(lane, cl));
+        const int x0 = min((int)f, p.sw - 1);
+        s_cx[lane] = x0 - x_lo;
+        s_lx[lane] = fminf(fmaxf(__fsub_rn(f, (float)x0), 0.f), 1.f);
+    } else if (warp == 1) {
+        const float f = src_index(sy, ty0 + min(lane, rl));
+        const int y0 = min((int)f, p.sh - 1);
+        s_r0[lane] = y0 - y_lo;
+        s_r1[lane] = min(y0 + 1, p.sh - 1) - y_lo;
+        s_ly[lane] = fminf(fmaxf(__fsub_rn(f, (float)y0), 0.f), 1.f);
+    }
+    // stage the window (every staged row lies inside the image; only the last column needs the clamp)
+    const int total = nrows * gpr;
+    const unsigned inv = ((1u << 20) + gpr - 1) / gpr;
+    const int rowb = 3 * p.sw;
+    for (int g = tid; g < total; g += kFThreads) {
+        const int r = (int)((g * inv) >> 20), k = g - r * gpr;
+        const int x = x_lo + 4 * k, bo = 3 * x;
+        const uint32_t* rp = reinterpret_cast<const uint32_t*>(img + (long long)(y_lo + r) * p.pitch) + (bo >> 2);
+        uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+        if (bo < rowb) w0 = __ldg(rp);
+        if (bo + 4 < rowb) w1 = __ldg(rp + 1);
+        if (bo + 8 < rowb) w2 = __ldg(rp + 2);
+        if (bo + 12 < rowb) w3 = __ldg(rp + 3);
+        uint32_t a[4] = {__byte_perm(w0, w1, 0x4130), __byte_perm(w0, w1, 0x7463),
+                         __byte_perm(w1, w2, 0x6352), __byte_perm(w2, w3, 0x5241)};
+        uint32_t c[4] = {__byte_perm(w0, w1, 0x0052), __byte_perm(w1, w2, 0x0041),
+                         __byte_perm(w2, w2, 0x0030), __byte_perm(w2, w3, 0x0063)};
+        if (x + 4 >= p.sw) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (x + i + 1 >= p.sw) {     // x1 = min(x0 + 1, in - 1): the pair's second pixel is the first one
+                    a[i] = __byte_perm(a[i], 0, 0x2200);
+                    c[i] = __byte_perm(c[i], 0, 0x4400);
+                }
+            }
+        }
+        uint4* d = reinterpret_cast<uint4*>(s_rec + r * pitch + 4 * k);
+        d[0] = make_uint4(a[0], c[0], a[1], c[1]);
+        d[1] = make_uint4(a[2], c[2], a[3], c[3]);
+    }
+    __syncthreads();
+
+    const int ox = tx0 + lane;
+    const int r0w = warp * kRowsPerWarp;
+    if (ox >= p.ow || ty0 + r0w >= p.oh) return;
+    const int cx = s_cx[lane];
+    const float lx1 = s_lx[lane], lx0 = __fsub_rn(1.0f, lx1);
+    const float na0 = p.mean[0], na1 = p.mean[1], na2 = p.mean[2];   // a, b of v*a + b (identity: 1/255... see launcher)
+    const float nb0 = p.stdv[0], nb1 = p.stdv[1], nb2 = p.stdv[2];
+    unsigned i0, i1, i2, step;
+    if (p.layout == LH_LAYOUT_CHW) {
+        const unsigned plane = (unsigned)(p.oh * p.ow);
+        i0 = ((unsigned)(n * 3) * p.oh + (ty0 + r0w)) * p.ow + ox;
+        i1 = i0 + plane; i2 = i1 + plane;
+        step = (unsigned)p.ow;
+    } else {
+        i0 = (((unsigned)n * p.oh + (ty0 + r0w)) * p.ow + ox) * 3u;
+        i1 = i0 + 1; i2 = i0 + 2;
+        step = 3u * (unsigned)p.ow;
+    }
+    if (p.chan_order == LH_CHAN_BGR) { const unsigned t = i0; i0 = i2; i2 = t; }
+    const int rows = min(kRowsPerWarp, p.oh - (ty0 + r0w));
+#pragma unroll
+    for (int j = 0; j < kRowsPerWarp; ++j) {
+        if (j >= rows) break;
+        const int r = r0w + j;
+        const float ly1 = s_ly[r], ly0 = __fsub_rn(1.0f, ly1);
+        const uint2 t0 = s_rec[s_r0[r] * pitch + cx], t1 = s_rec[s_r1[r] * pitch + cx];
+        auto lerp2 = [&](uint32_t w0_, uint32_t w1_, int sh_) {
+            const float p00 = (float)((w0_ >> sh_) & 0xffu), p01 = (float)((w0_ >> (sh_ + 8)) & 0xffu);
+            const float p10 = (float)((w1_ >> sh_) & 0xffu), p11 = (float)((w1_ >> (sh_ + 8)) & 0xffu);
+            const float top = fmaf(lx1, p01, lx0 * p00), bot = fmaf(lx1, p11, lx0 * p10);
+            return fmaf(ly1, bot, ly0 * top);
+        };
+        const float vr = lerp2(t0.x, t1.x, 0), vg = lerp2(t0.x, t1.x, 16), vb = lerp2(t0.y, t1.y, 0);
+        __stcs(p.dst + i0, fmaf(vr, na0, nb0));
+        __stcs(p.dst + i1, fmaf(vg, na1, nb1));
+        __stcs(p.dst + i2, fmaf(vb, na2, nb2));
+        i0 += step; i1 += step; i2 += step;
+    }
+}
+
 __global__ void norm_lut_kernel(const double* gain, int tables, int normalise, float m0, float m1, float m2,
                                 float s0, float s1, float s2, float* lut) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -665,7 +787,23 @@ extern "C" int lh_warp_normalize(const uint8_t* src, int64_t src_img_stride, int
     dim3 grid((out_w + kTile - 1) / kTile, (out_h + kTile - 1) / kTile, N), block(kWThreads);
     cudaStream_t st = (cudaStream_t)stream;
     if (interp == LH_INTERP_TORCH) {
-        resize_torch_kernel<<<grid, block, 0, st>>>(p);
+        const bool words = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)src_pitch | (uintptr_t)src_img_stride) & 3u) == 0;
+        // source records needed by one 32x32 output tile: (32 * in/out + 2 + alignment)^2 must fit the staging buffer
+        const double fx = 32.0 * src_w / out_w + 8.0, fy = 32.0 * src_h / out_h + 3.0;
+        const long long per_img = 3LL * out_h * out_w;
+        const bool fits = (((int)fx + 7) / 8 * 8 + 6) * (long long)((int)fy + 1) <= kRMaxPos;
+        if (words && fits && !flip && !chan_gain && per_img * N < (1LL << 31)) {
+            WarpParams q = p;
+            for (int i = 0; i < 3; ++i) {        // v (byte units) * a + b
+                const double sd = mean_std ? (double)mean_std[3 + i] : 1.0, mu = mean_std ? (double)mean_std[i] : 0.0;
+                q.mean[i] = (float)(1.0 / (255.0 * sd));
+                q.stdv[i] = (float)(-mu / sd);
+            }
+            dim3 fgrid((out_w + kTileW - 1) / kTileW, (out_h + kTileH - 1) / kTileH, N);
+            resize_pairs_kernel<<<fgrid, kFThreads, 0, st>>>(q);
+        } else {
+            resize_torch_kernel<<<grid, block, 0, st>>>(p);
+        }
     } else {
         const bool stage = aligned16(src) && (src_pitch % 16 == 0) && (src_img_stride % 16 == 0);
         const bool words = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)src_pitch | (uintptr_t)src_img_stride) & 3u) == 0;
