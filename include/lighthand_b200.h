@@ -61,7 +61,13 @@ int lh_device_query(int device, int* sm_count, int* cc_major, int* cc_minor, uin
 /* Normalisation table for LH_INTERP_CV2_U8: lut[i][c][v] = ((clip(v*gain[i][c],0,255))/255 - mean[c])/std[c]
  * evaluated with IEEE float32/float64 ops in torch's order (bit-exact).  chan_gain dev [N,3] double or
  * NULL (then one table, N ignored).  mean_std host [6] = mean[3],std[3]; NULL -> identity table
- * (value 0..255 after gain/clip, no /255).  lut dev [(chan_gain?N:1)][3][256] float. */
+ * (value 0..255 after gain/clip, no /255).  lut dev [(chan_gain?N:1)][3][256] float.
+ *
+ * lh_warp_normalize, LH_INTERP_CV2_U8: the warped uint8 pixel is always cv2's, bit for bit.  With `lut` the
+ * float result is the table entry (bit-identical to ToTensor + Normalize); with lut == NULL it is one fused
+ * multiply-add v*a + b, a = 1/(255 std), b = -mean/std (<= 2 ulp from the former; mean_std == NULL: the raw
+ * 0..255 value).  chan_gain requires the table.  LH_INTERP_TORCH computes torch's bilinear resize
+ * (align_corners = False, no antialias) to ~3 ulp (exact operation order when flip / chan_gain is given). */
 int lh_norm_lut_build(const double* chan_gain, int N, const float* mean_std, float* lut, lh_stream_t stream);
 
 int lh_warp_normalize(const uint8_t* src,        /* dev N HWC RGB uint8 images                   */
@@ -71,7 +77,7 @@ int lh_warp_normalize(const uint8_t* src,        /* dev N HWC RGB uint8 images  
                       const uint8_t* flip,       /* dev [N] 0/1 or NULL                           */
                       const double* chan_gain,   /* dev [N,3] or NULL                             */
                       const float* mean_std,     /* host [6] or NULL (identity)                   */
-                      const float* lut,          /* dev table from lh_norm_lut_build (CV2_U8 only)*/
+                      const float* lut,          /* dev table from lh_norm_lut_build, or NULL     */
                       int interp, int chan_order, int out_layout,
                       float* dst, int N, int out_h, int out_w, lh_stream_t stream);
 
