@@ -28,6 +28,16 @@ __device__ unsigned long long g_lh_oob = 0ull;
 #define LH_BOUNDS(cond) do { } while (0)
 #endif
 
+#ifdef LH_PHASE_TIMING
+// debug build: per-phase clock64() sums over all CTAs of the fast kernel (tools/phase_timing.py)
+__device__ unsigned long long g_lh_phase[4] = {0ull, 0ull, 0ull, 0ull};
+#define LH_TICK(var) const long long var = clock64()
+#define LH_PHASE_ADD(i, a, b) do { if (threadIdx.x == 0) atomicAdd(&g_lh_phase[i], (unsigned long long)((b) - (a))); } while (0)
+#else
+#define LH_TICK(var) do { } while (0)
+#define LH_PHASE_ADD(i, a, b) do { } while (0)
+#endif
+
 constexpr int kTile = 32;
 constexpr int kWThreads = 256;
 constexpr int kStageBytes = 24 * 1024;
@@ -400,6 +410,10 @@ __device__ __forceinline__ void warp_rows(const WarpParams& p, const TileBox& bx
 #ifndef LH_FAST_MINB
 #define LH_FAST_MINB 8
 #endif
+#ifndef LH_STAGE_DEPTH
+#define LH_STAGE_DEPTH 3
+#endif
+constexpr int kStageDepth = LH_STAGE_DEPTH;   // groups of 4 records whose loads a thread keeps in flight together
 template <int NORM>
 __global__ void __launch_bounds__(kFThreads, LH_FAST_MINB) warp_pairs_kernel(const WarpParams p) {
     __shared__ __align__(16) uint2 s_rec[kMaxPos];
@@ -413,6 +427,7 @@ __global__ void __launch_bounds__(kFThreads, LH_FAST_MINB) warp_pairs_kernel(con
     const int n = blockIdx.z;
     const int tx0 = blockIdx.x * kTileW, ty0 = blockIdx.y * kTileH;
     const uint8_t* img = p.src + (long long)n * p.img_stride;
+    LH_TICK(t_begin);
 
     // ---- phase 1: column terms (warp 0), row terms (next kTileH/32 warps), tile footprint (one more lane);
     // every participating thread inverts the 2x3 matrix itself (a handful of FP64 ops): a single barrier
@@ -472,55 +487,63 @@ __global__ void __launch_bounds__(kFThreads, LH_FAST_MINB) warp_pairs_kernel(con
         for (int i = tid; i < 768; i += kFThreads) s_lut[i] = lut[i];
     }
     __syncthreads();
+    LH_TICK(t_pro);
+    LH_PHASE_ADD(0, t_begin, t_pro);
     const TileBox bx = s_box;
     const bool staged = bx.flags & 1;
 
-    // ---- phase 2: stage the footprint as position records ---------------------------------------------
+    // ---- phase 2: stage the footprint as position records.  A thread owns groups of 4 records; the loads of
+    // up to kStageDepth groups are issued before the first is converted, so a typical tile (<= 384 groups)
+    // pays ONE global-load round trip (phase timing showed two with a compiler-unrolled loop: the remainder
+    // iteration ran first) ---------------------------------------------------------------------------------------
     if (staged) {
-        const int gpr = bx.gpr, total = bx.total;       // total <= kMaxPos / 4
-        const unsigned inv = bx.inv;
-        if (bx.flags & 4) {
-            // interior tile: every staged byte lies inside the image, no predicates, no masks
-            const uint8_t* org = img + (long long)bx.loy * p.pitch + 3 * bx.cx0;
-#pragma unroll 2
-            for (int g = tid; g < total; g += kFThreads) {
-                const int r = (int)((g * inv) >> 20), k = g - r * gpr;
-                const uint32_t* rp = reinterpret_cast<const uint32_t*>(org + (long long)r * p.pitch) + 3 * k;
-                const uint32_t w0 = __ldg(rp), w1 = __ldg(rp + 1), w2 = __ldg(rp + 2), w3 = __ldg(rp + 3);
-                uint4* d = reinterpret_cast<uint4*>(s_rec + r * bx.pitch + 4 * k);
-                LH_BOUNDS(r >= 0 && r < bx.nrows && k >= 0 && 4 * k + 3 < bx.pitch && r * bx.pitch + 4 * k + 3 < kMaxPos);
-                d[0] = make_uint4(__byte_perm(w0, w1, 0x4130), __byte_perm(w0, w1, 0x0052),
-                                  __byte_perm(w0, w1, 0x7463), __byte_perm(w1, w2, 0x0041));
-                d[1] = make_uint4(__byte_perm(w1, w2, 0x6352), __byte_perm(w2, w2, 0x0030),
-                                  __byte_perm(w2, w3, 0x5241), __byte_perm(w2, w3, 0x0063));
-            }
-        } else {
-            const int rowb = 3 * p.sw;
-            for (int g = tid; g < total; g += kFThreads) {
-                const int r = (int)((g * inv) >> 20), k = g - r * gpr;
-                const int y = bx.loy + r, x = bx.cx0 + 4 * k;
-                uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-                const bool yin = (y >= 0) & (y < p.sh);
-                const int bo = 3 * x;                // byte offset of the group in the row (multiple of 4)
-                if (yin) {
-                    const uint32_t* rp = reinterpret_cast<const uint32_t*>(img + (long long)y * p.pitch);
-                    // a word is loaded when it starts inside [0, rowb); bytes of it beyond the row are masked below
-                    if (bo >= 0 && bo < rowb) w0 = __ldg(rp + (bo >> 2));
-                    if (bo + 4 >= 0 && bo + 4 < rowb) w1 = __ldg(rp + (bo >> 2) + 1);
-                    if (bo + 8 >= 0 && bo + 8 < rowb) w2 = __ldg(rp + (bo >> 2) + 2);
-                    if (bo + 12 >= 0 && bo + 12 < rowb) w3 = __ldg(rp + (bo >> 2) + 3);
+        const bool interior = bx.flags & 4;
+        const uint8_t* org = img + (long long)bx.loy * p.pitch + 3 * bx.cx0;
+        const int rowb = 3 * p.sw;
+        for (int g0 = tid; g0 < bx.total; g0 += kStageDepth * kFThreads) {
+            uint32_t w[kStageDepth][4];
+#pragma unroll
+            for (int i = 0; i < kStageDepth; ++i) {
+                const int g = g0 + i * kFThreads;
+                w[i][0] = w[i][1] = w[i][2] = w[i][3] = 0u;
+                if (g < bx.total) {
+                    const int r = (int)((g * bx.inv) >> 20), k = g - r * bx.gpr;
+                    if (interior) {     // every staged byte lies inside the image: no predicates
+                        const uint32_t* rp = reinterpret_cast<const uint32_t*>(org + (long long)r * p.pitch) + 3 * k;
+                        w[i][0] = __ldg(rp); w[i][1] = __ldg(rp + 1); w[i][2] = __ldg(rp + 2); w[i][3] = __ldg(rp + 3);
+                    } else {
+                        const int y = bx.loy + r, bo = 3 * (bx.cx0 + 4 * k);   // byte offset in the row (multiple of 4)
+                        if (y >= 0 && y < p.sh) {
+                            const uint32_t* rp = reinterpret_cast<const uint32_t*>(img + (long long)y * p.pitch);
+                            // a word is loaded when it starts inside [0, rowb); bytes beyond the row are masked below
+                            if (bo >= 0 && bo < rowb) w[i][0] = __ldg(rp + (bo >> 2));
+                            if (bo + 4 >= 0 && bo + 4 < rowb) w[i][1] = __ldg(rp + (bo >> 2) + 1);
+                            if (bo + 8 >= 0 && bo + 8 < rowb) w[i][2] = __ldg(rp + (bo >> 2) + 2);
+                            if (bo + 12 >= 0 && bo + 12 < rowb) w[i][3] = __ldg(rp + (bo >> 2) + 3);
+                        }
+                    }
                 }
+            }
+#pragma unroll
+            for (int i = 0; i < kStageDepth; ++i) {
+                const int g = g0 + i * kFThreads;
+                if (g >= bx.total) continue;
+                const int r = (int)((g * bx.inv) >> 20), k = g - r * bx.gpr;
+                const uint32_t w0 = w[i][0], w1 = w[i][1], w2 = w[i][2], w3 = w[i][3];
                 uint32_t a[4] = {__byte_perm(w0, w1, 0x4130), __byte_perm(w0, w1, 0x7463),
                                  __byte_perm(w1, w2, 0x6352), __byte_perm(w2, w3, 0x5241)};
                 uint32_t c[4] = {__byte_perm(w0, w1, 0x0052), __byte_perm(w1, w2, 0x0041),
                                  __byte_perm(w2, w2, 0x0030), __byte_perm(w2, w3, 0x0063)};
+                if (!interior) {
+                    const int y = bx.loy + r, x = bx.cx0 + 4 * k;
+                    const bool yin = (y >= 0) & (y < p.sh);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    // zero the halves that lie outside the image (constant border 0)
-                    const bool va = yin && (x + i >= 0) && (x + i < p.sw);
-                    const bool vb = yin && (x + i + 1 >= 0) && (x + i + 1 < p.sw);
-                    const uint32_t m = (va ? 0x00ff00ffu : 0u) | (vb ? 0xff00ff00u : 0u);
-                    a[i] &= m; c[i] &= m;
+                    for (int q = 0; q < 4; ++q) {   // zero the halves that lie outside the image (constant border 0)
+                        const bool va = yin && (x + q >= 0) && (x + q < p.sw);
+                        const bool vb = yin && (x + q + 1 >= 0) && (x + q + 1 < p.sw);
+                        const uint32_t m = (va ? 0x00ff00ffu : 0u) | (vb ? 0xff00ff00u : 0u);
+                        a[q] &= m; c[q] &= m;
+                    }
                 }
                 uint4* d = reinterpret_cast<uint4*>(s_rec + r * bx.pitch + 4 * k);
                 LH_BOUNDS(r >= 0 && r < bx.nrows && k >= 0 && 4 * k + 3 < bx.pitch && r * bx.pitch + 4 * k + 3 < kMaxPos);
@@ -530,6 +553,8 @@ __global__ void __launch_bounds__(kFThreads, LH_FAST_MINB) warp_pairs_kernel(con
         }
     }
     __syncthreads();
+    LH_TICK(t_stage);
+    LH_PHASE_ADD(1, t_pro, t_stage);
 
     // ---- phase 3: lane = output column, warp w renders tile rows 8w .. 8w+7 ---------------------------------
     const int ox = tx0 + lane;
@@ -538,6 +563,9 @@ __global__ void __launch_bounds__(kFThreads, LH_FAST_MINB) warp_pairs_kernel(con
     if (!staged)            warp_rows<NORM, false, false>(p, bx, s_rec, s_lut, s_x0, s_y0, img, ad, bd, n, ox, ty0, warp);
     else if (bx.flags & 2)  warp_rows<NORM, true, true>(p, bx, s_rec, s_lut, s_x0, s_y0, img, ad, bd, n, ox, ty0, warp);
     else                    warp_rows<NORM, false, true>(p, bx, s_rec, s_lut, s_x0, s_y0, img, ad, bd, n, ox, ty0, warp);
+    LH_TICK(t_rows);
+    LH_PHASE_ADD(2, t_stage, t_rows);          // warp 0's render time (stores issued, not necessarily drained)
+    LH_PHASE_ADD(3, t_begin, t_rows);
 }
 
 // LH_INTERP_TORCH: ToTensor -> Resize(bilinear, align_corners=False, no antialias) -> Normalize.
@@ -734,6 +762,14 @@ static void fma_coeffs(WarpParams& p, const float* mean_std) {
         p.stdv[i] = (float)(-(double)mean_std[i] / sd);
     }
 }
+
+#ifdef LH_PHASE_TIMING
+extern "C" void lh_debug_phase_cycles(unsigned long long* out4, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out4, g_lh_phase, 4 * sizeof(unsigned long long));
+    if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(g_lh_phase, z, sizeof(z)); }
+}
+#endif
 
 #ifdef LH_DEBUG_BOUNDS
 extern "C" unsigned long long lh_debug_oob_count(void) {
