@@ -61,3 +61,16 @@ def test_ops_refuse_to_run_without_cuda():
         ops.decode(torch.zeros(1, 21, 64, 64))
     with pytest.raises(ops.LighthandError):
         get_max_preds(np.zeros((1, 21, 64, 64), np.float32))
+
+
+def test_header_is_plain_c_and_the_c_host_links(tmp_path):
+    """include/lighthand_b200.h compiles as C11 and the plain-C host (tests/c/abi_host_demo.c, run by the gpu
+    suite) links against the library with no C++ or torch symbols needed."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    libdir = os.path.join(ROOT, "lighthand_b200")
+    subprocess.run(["gcc", "-std=c11", "-O1", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "abi_host_demo.c"), "-o", str(tmp_path / "demo"), "-L", libdir,
+                    "-llighthand_b200", "-lm"], check=True)
