@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define LH_ABI_VERSION 2
+#define LH_ABI_VERSION 3
 
 #define LH_OK            0
 #define LH_EINVAL       (-1)  /* bad size / enum value */
@@ -190,6 +190,47 @@ int lh_pck_curve_accum(const float* pred_xy, const float* gt, int gt_stride,
                        int64_t N, int J, const double* thr_sorted, int K, int method, int use_vis,
                        unsigned long long* hist, unsigned long long* n_valid,
                        unsigned long long* n_all, double* sum_d, lh_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * FreiHAND image path.  Replaces, batched:
+ *   crop / myimrotate / myimresize        src/utils/image_ops.py:25-56, 97-131
+ *   HandMeshTSVDataset.rgb_processing     src/datasets/frei_dataloader.py:134-147   (flip is always 0, :107)
+ *   Resize((256,256)) + Normalize + [(2,1,0)]   src/datasets/frei_dataloader.py:279-283, 338
+ * crop()'s integer window bookkeeping (transform(..., invert=1) via torch.inverse, int truncation, rotation
+ * padding; image_ops.py:99-106) is host logic and arrives per sample in lh_frei_desc
+ * (lighthand_b200/utils/image_ops.py fills it exactly as the reference computes it).
+ * Accuracy: the rotation stage is bit-identical to cv2 (fixed-point grid, exact float32 sums); the cv2.resize
+ * stage floors its coordinates in double like OpenCV and blends in float32: <= 1e-4 on the 0..255 scale
+ * against the reference's float64 (bar for this path: 1 LSB).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct lh_frei_desc {
+    int32_t ulx, uly;       /* window origin in the source image (rotation padding included)            */
+    int32_t cw, ch;         /* canvas size br - ul (rotation padding included)                           */
+    int32_t pad;            /* rotation padding (image_ops.py:103); ignored unless rotated               */
+    int32_t rotated;        /* rot != 0                                                                  */
+    double iM[6];           /* rotated: cv2.getRotationMatrix2D(((cw-1)/2, (ch-1)/2), rot, 1.0) inverted in double the
+                               way cv2.warpAffine inverts it (dst -> src, row-major)                       */
+    double scale_x, scale_y;/* cv2.resize's 1.0 / ((double)res / iw), 1.0 / ((double)res / ih) with
+                               iw = cw - 2 pad, ih = ch - 2 pad (pad counted only when rotated)            */
+    float pn[3];            /* per-channel pixel noise (frei_dataloader.py:118)                          */
+    int32_t reserved;
+    int64_t scratch_off;    /* float offset of this sample's rotated canvas [(ch-2pad),(cw-2pad),3] in `scratch` */
+} lh_frei_desc;
+
+/* rgb_processing for N images: out dev [N,3,res,res] float32 in 0..1 (CHW, /255, noise applied).
+ * desc dev [N]; rot_index dev int32 [n_rot] = indices of the samples with rotated != 0 (NULL: every sample is
+ * visited and the flag decides); scratch dev float (sum of the rotated canvases) or NULL when max_rot_px == 0;
+ * max_rot_px = max over rotated samples of (cw-2pad)*(ch-2pad) (0: no sample is rotated). */
+int lh_frei_rgb_processing(const uint8_t* src, int64_t src_img_stride, int src_h, int src_w, int src_pitch,
+                           const lh_frei_desc* desc, int N, int res, const int32_t* rot_index, int n_rot,
+                           float* scratch, int64_t max_rot_px, float* out, lh_stream_t stream);
+
+/* transforms.Resize((out_h,out_w)) on a float CHW batch (bilinear, align_corners=False, no antialias; ATen's
+ * float32 operation order, within ~1 ulp of torch) + Normalize as one multiply-add (mean_std host [6] or NULL;
+ * <= 2 ulp from (x - mean) / std) + channel order.
+ * src dev [N,3,src_h,src_w]; dst dev [N,3,out_h,out_w]. */
+int lh_resize_normalize_f32(const float* src, int N, int src_h, int src_w, const float* mean_std, int chan_order,
+                            float* dst, int out_h, int out_w, lh_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Host-buffer pipeline context (what a non-torch host binds; also the e2e benchmark path).

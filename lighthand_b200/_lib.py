@@ -57,6 +57,14 @@ class PipelineIO(C.Structure):
     ]
 
 
+class FreiDesc(C.Structure):
+    _fields_ = [
+        ("ulx", C.c_int32), ("uly", C.c_int32), ("cw", C.c_int32), ("ch", C.c_int32), ("pad", C.c_int32),
+        ("rotated", C.c_int32), ("iM", C.c_double * 6), ("scale_x", C.c_double), ("scale_y", C.c_double), ("pn", c_f * 3), ("reserved", C.c_int32),
+        ("scratch_off", c_i64),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/lighthand_b200.h declares
 PROTOTYPES = {
     "lh_abi_version": (c_i, []),
@@ -73,6 +81,8 @@ PROTOTYPES = {
     "lh_pck_epe_batch": (c_i, [c_p, c_p, c_i, c_i64, c_i, c_f, c_i, c_i, c_p, c_p, c_p]),
     "lh_pck_curve_accum": (c_i, [c_p, c_p, c_i, c_p, c_p, c_i, c_i64, c_i, c_p, c_i, c_i, c_i,
                                  c_p, c_p, c_p, c_p, c_p]),
+    "lh_frei_rgb_processing": (c_i, [c_p, c_i64, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_i, c_p, c_i64, c_p, c_p]),
+    "lh_resize_normalize_f32": (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, c_p, c_i, c_i, c_p]),
     "lh_pipeline_create": (c_i, [C.POINTER(PipelineCfg), c_p, c_i, C.POINTER(c_p)]),
     "lh_pipeline_destroy": (None, [c_p]),
     "lh_pipeline_input_dev": (c_p, [c_p]),
@@ -105,7 +115,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so is stale
         fn.restype = res
         fn.argtypes = args
-    if lib.lh_abi_version() != 2:
+    if lib.lh_abi_version() != 3:
         raise LighthandError("liblighthand_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

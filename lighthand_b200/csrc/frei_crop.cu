@@ -1,0 +1,214 @@
+// FreiHAND image path: the multi-stage crop of src/utils/image_ops.py:97-131 and the
+// tail of HandMeshTSVDataset.__getitem__ (src/datasets/frei_dataloader.py:134-147, 276-283, 338), batched.
+//
+//   stage R (rotated samples only)  myimrotate  image_ops.py:25-44   cv2.warpAffine of the zero-padded window about
+//                                   its centre on cv2's 1/32-px fixed-point grid; only the part that survives
+//                                   new_img[pad:-pad, pad:-pad] is computed, into a float32 scratch canvas.  The
+//                                   values are sums of (uint8 x 10-bit dyadic weights): exact in float32, i.e.
+//                                   bit-identical to cv2's float64 result.
+//   stage S                         myimresize  image_ops.py:46-56   cv2.resize(INTER_LINEAR) of the (rotated)
+//                                   canvas to res x res: half-pixel coordinates and floor in double like OpenCV,
+//                                   blend in float32; then rgb_processing's pixel noise + clip + /255, CHW.
+//   stage T                         transforms.Resize + Normalize + channels (2,1,0): lh_resize_normalize_f32.
+//
+// The integer window bookkeeping of crop() (transform(..., invert=1) through torch.inverse, int truncation, the
+// rotation padding) is host logic: it arrives per sample in lh_frei_desc (lighthand_b200/utils/image_ops.py).
+// The un-rotated window is never materialised: stage S reads the uint8 image through the window's zero padding.
+#include "lh_common.cuh"
+
+namespace lh {
+
+constexpr int kFreiThreads = 256;
+
+// pixel (cx, cy) of the zero float64 canvas crop() fills from the image (image_ops.py:107-122)
+__device__ __forceinline__ void canvas_px(const uint8_t* img, int pitch, int sh, int sw, const lh_frei_desc& d,
+                                          int cx, int cy, float (&v)[3]) {
+    v[0] = v[1] = v[2] = 0.f;
+    if (cx < 0 || cy < 0 || cx >= d.cw || cy >= d.ch) return;
+    const int x = d.ulx + cx, y = d.uly + cy;
+    if (x < 0 || y < 0 || x >= sw || y >= sh) return;
+    const uint8_t* q = img + (long long)y * pitch + 3 * x;
+    v[0] = (float)__ldg(q); v[1] = (float)__ldg(q + 1); v[2] = (float)__ldg(q + 2);
+}
+
+__global__ void __launch_bounds__(kFreiThreads) frei_rotate_kernel(const uint8_t* __restrict__ src, long long img_stride,
+                                                                   int sh, int sw, int pitch,
+                                                                   const lh_frei_desc* __restrict__ desc,
+                                                                   const int32_t* __restrict__ rot_index,
+                                                                   float* __restrict__ scratch) {
+    const int n = rot_index ? rot_index[blockIdx.y] : blockIdx.y;
+    const lh_frei_desc d = desc[n];
+    if (!d.rotated) return;
+    const double* s_im = d.iM;
+    const int iw = d.cw - 2 * d.pad, ih = d.ch - 2 * d.pad;
+    const uint8_t* img = src + (long long)n * img_stride;
+    float* out = scratch + d.scratch_off;
+    for (int idx = blockIdx.x * kFreiThreads + threadIdx.x; idx < iw * ih; idx += gridDim.x * kFreiThreads) {
+        const int y = idx / iw, x = idx - y * iw;
+        const int dx = x + d.pad, dy = y + d.pad;          // position in the padded canvas warpAffine renders
+        const int X = (row_term(s_im[1], s_im[2], dy) + col_term(s_im[0], dx)) >> 5;
+        const int Y = (row_term(s_im[4], s_im[5], dy) + col_term(s_im[3], dx)) >> 5;
+        const int ix = clamp_i(X >> 5, -32768, 32767), iy = clamp_i(Y >> 5, -32768, 32767);   // cv2 stores shorts
+        const float fx = (float)(X & 31) * 0.03125f, fy = (float)(Y & 31) * 0.03125f;
+        const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+        float p00[3], p01[3], p10[3], p11[3];
+        canvas_px(img, pitch, sh, sw, d, ix, iy, p00);
+        canvas_px(img, pitch, sh, sw, d, ix + 1, iy, p01);
+        canvas_px(img, pitch, sh, sw, d, ix, iy + 1, p10);
+        canvas_px(img, pitch, sh, sw, d, ix + 1, iy + 1, p11);
+#pragma unroll
+        for (int c = 0; c < 3; ++c)    // every product and partial sum is exact in float32 (<= 18 bits)
+            out[(size_t)idx * 3 + c] = p00[c] * w00 + p01[c] * w01 + p10[c] * w10 + p11[c] * w11;
+    }
+}
+
+// cv2.resize's source index / weight for destination index d (resize.cpp, INTER_LINEAR, CV_64F): double
+// arithmetic without contraction, edge clamp
+__device__ __forceinline__ void cv2_linear_axis(int d, int ssize, double scale, int& s0, int& s1, float& w0, float& w1) {
+    double f = __dsub_rn(__dmul_rn(__dadd_rn((double)d, 0.5), scale), 0.5);
+    int s = (int)floor(f);
+    f = __dsub_rn(f, (double)s);
+    if (s < 0) { f = 0.0; s = 0; }
+    if (s >= ssize - 1) { f = 0.0; s = ssize - 1; }
+    s0 = s; s1 = min(s + 1, ssize - 1);
+    w0 = (float)__dsub_rn(1.0, f); w1 = (float)f;
+}
+
+__global__ void __launch_bounds__(kFreiThreads) frei_resize_kernel(const uint8_t* __restrict__ src, long long img_stride,
+                                                                   int sh, int sw, int pitch,
+                                                                   const lh_frei_desc* __restrict__ desc,
+                                                                   const float* __restrict__ scratch, int res,
+                                                                   float* __restrict__ dst) {
+    const int n = blockIdx.z;
+    const lh_frei_desc d = desc[n];
+    const int pad = d.rotated ? d.pad : 0;
+    const int iw = d.cw - 2 * pad, ih = d.ch - 2 * pad;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * (kFreiThreads / 32) + (threadIdx.x >> 5);
+    if (x >= res || y >= res) return;
+    float* o = dst + (size_t)n * 3 * res * res + (size_t)y * res + x;
+    if (iw <= 0 || ih <= 0) { o[0] = 0.f; o[(size_t)res * res] = 0.f; o[2 * (size_t)res * res] = 0.f; return; }
+    const double scx = d.scale_x, scy = d.scale_y;     // 1 / (res / iw), 1 / (res / ih): host, double, like OpenCV
+    int x0, x1, y0, y1;
+    float a0, a1, b0, b1;
+    cv2_linear_axis(x, iw, scx, x0, x1, a0, a1);
+    cv2_linear_axis(y, ih, scy, y0, y1, b0, b1);
+    float p00[3], p01[3], p10[3], p11[3];
+    if (d.rotated) {
+        const float* r0 = scratch + d.scratch_off + (size_t)y0 * iw * 3;
+        const float* r1 = scratch + d.scratch_off + (size_t)y1 * iw * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            p00[c] = __ldg(r0 + 3 * x0 + c); p01[c] = __ldg(r0 + 3 * x1 + c);
+            p10[c] = __ldg(r1 + 3 * x0 + c); p11[c] = __ldg(r1 + 3 * x1 + c);
+        }
+    } else {
+        const uint8_t* img = src + (long long)n * img_stride;
+        canvas_px(img, pitch, sh, sw, d, x0, y0, p00);
+        canvas_px(img, pitch, sh, sw, d, x1, y0, p01);
+        canvas_px(img, pitch, sh, sw, d, x0, y1, p10);
+        canvas_px(img, pitch, sh, sw, d, x1, y1, p11);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float top = fmaf(p01[c], a1, p00[c] * a0), bot = fmaf(p11[c], a1, p10[c] * a0);   // rows first ...
+        float v = fmaf(bot, b1, top * b0);                                                       // ... then columns
+        v = fminf(255.0f, fmaxf(0.0f, v * d.pn[c]));          // pixel noise + clip (frei_dataloader.py:142-144)
+        o[(size_t)c * res * res] = v * (1.0f / 255.0f);       // CHW float32 / 255 (:146), <= 1 ulp from the division
+    }
+}
+
+// transforms.Resize((oh, ow)) on a float CHW tensor (bilinear, align_corners = False, no antialias, ATen's
+// float32 operation order) + Normalize (one fused multiply-add, <= 2 ulp from (x - mean) / std) + optional channel
+// reversal (frei_dataloader.py:279-283, 338)
+__global__ void __launch_bounds__(kFreiThreads) resize_f32_kernel(const float* __restrict__ src, int sh, int sw,
+                                                                  float* __restrict__ dst, int oh, int ow, float sy, float sx,
+                                                                  float a0, float a1, float a2, float b0, float b1,
+                                                                  float b2, int chan_order, int vec) {
+    // a thread renders 4 consecutive output columns of one row, all 3 channels: the row terms are computed once
+    // and every channel leaves as one 16-byte streaming store
+    const int n = blockIdx.z;
+    const int ox = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4, oy = blockIdx.y * (kFreiThreads / 64) + (threadIdx.x >> 6);
+    if (ox >= ow || oy >= oh) return;
+    float fy = fmaf(sy, __fadd_rn((float)oy, 0.5f), -0.5f);      // ATen: one fused multiply-add; sy = in / out (float32)
+    fy = fy < 0.f ? 0.f : fy;
+    const int y0 = min((int)fy, sh - 1), y1 = min(y0 + 1, sh - 1);
+    const float ly1 = fminf(fmaxf(__fsub_rn(fy, (float)y0), 0.f), 1.f), ly0 = __fsub_rn(1.0f, ly1);
+    int x0[4], x1[4];
+    float lx0[4], lx1[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float fx = fmaf(sx, __fadd_rn((float)(ox + k), 0.5f), -0.5f);
+        fx = fx < 0.f ? 0.f : fx;
+        x0[k] = min((int)fx, sw - 1); x1[k] = min(x0[k] + 1, sw - 1);
+        lx1[k] = fminf(fmaxf(__fsub_rn(fx, (float)x0[k]), 0.f), 1.f); lx0[k] = __fsub_rn(1.0f, lx1[k]);
+    }
+    const float na[3] = {a0, a1, a2}, nb[3] = {b0, b1, b2};      // Normalize as v * a + b, a = 1/std, b = -mean/std
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float* r0 = src + (((size_t)n * 3 + c) * sh + y0) * sw;
+        const float* r1 = src + (((size_t)n * 3 + c) * sh + y1) * sw;
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float top = __fadd_rn(__fmul_rn(lx0[k], __ldg(r0 + x0[k])), __fmul_rn(lx1[k], __ldg(r0 + x1[k])));
+            const float bot = __fadd_rn(__fmul_rn(lx0[k], __ldg(r1 + x0[k])), __fmul_rn(lx1[k], __ldg(r1 + x1[k])));
+            v[k] = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+            v[k] = fmaf(v[k], na[c], nb[c]);
+        }
+        const int co = (chan_order == LH_CHAN_BGR) ? 2 - c : c;
+        float* o = dst + (((size_t)n * 3 + co) * oh + oy) * ow + ox;
+        if (vec) {
+            stg_cs4(o, make_float4(v[0], v[1], v[2], v[3]));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (ox + k < ow) __stcs(o + k, v[k]);
+        }
+    }
+}
+
+}  // namespace lh
+
+extern "C" int lh_frei_rgb_processing(const uint8_t* src, int64_t src_img_stride, int src_h, int src_w, int src_pitch,
+                                      const lh_frei_desc* desc, int N, int res, const int32_t* rot_index, int n_rot,
+                                      float* scratch, int64_t max_rot_px, float* out, lh_stream_t stream) {
+    if (N < 0 || res <= 0 || src_h <= 0 || src_w <= 0 || src_pitch < 3 * src_w || max_rot_px < 0 || n_rot < 0 || n_rot > N)
+        return LH_EINVAL;
+    if (N == 0) return LH_OK;
+    if (!src || !desc || !out || (max_rot_px > 0 && !scratch)) return LH_ENULL;
+    if (N > 65535 || res > 32768 || max_rot_px > (int64_t)1 << 30) return LH_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (max_rot_px > 0) {
+        const int gx = (int)((max_rot_px + lh::kFreiThreads - 1) / lh::kFreiThreads);
+        const int ny = rot_index ? n_rot : N;      // with the list only the rotated samples get CTAs
+        if (ny > 0)
+            lh::frei_rotate_kernel<<<dim3(gx, ny), lh::kFreiThreads, 0, st>>>(src, (long long)src_img_stride, src_h, src_w,
+                                                                            src_pitch, desc, rot_index, scratch);
+        LH_CHECK_LAUNCH();
+    }
+    const int rows = lh::kFreiThreads / 32;
+    lh::frei_resize_kernel<<<dim3((res + 31) / 32, (res + rows - 1) / rows, N), lh::kFreiThreads, 0, st>>>(src, (long long)src_img_stride, src_h, src_w,
+                                                                   src_pitch, desc, scratch, res, out);
+    LH_CHECK_LAUNCH();
+    return LH_OK;
+}
+
+extern "C" int lh_resize_normalize_f32(const float* src, int N, int src_h, int src_w, const float* mean_std,
+                                       int chan_order, float* dst, int out_h, int out_w, lh_stream_t stream) {
+    if (N < 0 || src_h <= 0 || src_w <= 0 || out_h <= 0 || out_w <= 0) return LH_EINVAL;
+    if (chan_order != LH_CHAN_RGB && chan_order != LH_CHAN_BGR) return LH_EINVAL;
+    if (N == 0) return LH_OK;
+    if (!src || !dst) return LH_ENULL;
+    if (N > 65535 || out_h > 65535 * 4 || (int64_t)src_h * src_w > (int64_t)1 << 30) return LH_EINVAL;
+    const float* ms = mean_std;
+    const int rows = lh::kFreiThreads / 64;
+    const int vec = (out_w % 4 == 0) && lh::aligned16(dst);
+    float a[3] = {1.f, 1.f, 1.f}, b[3] = {0.f, 0.f, 0.f};
+    if (ms)
+        for (int c = 0; c < 3; ++c) { a[c] = 1.0f / ms[3 + c]; b[c] = -ms[c] / ms[3 + c]; }
+    const float sy = (float)src_h / (float)out_h, sx = (float)src_w / (float)out_w;     // ATen: float32 in / out
+    lh::resize_f32_kernel<<<dim3((out_w + 255) / 256, (out_h + rows - 1) / rows, N), lh::kFreiThreads, 0,
+                            (cudaStream_t)stream>>>(src, src_h, src_w, dst, out_h, out_w, sy, sx, a[0], a[1], a[2], b[0],
+                                                    b[1], b[2], chan_order, vec);
+    LH_CHECK_LAUNCH();
+    return LH_OK;
+}

@@ -49,6 +49,37 @@ __device__ __forceinline__ uint32_t order_key(float v) {
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
+
+// ---- cv2.warpAffine coordinate arithmetic, shared by the warp kernels -----------------
+__device__ __forceinline__ int clamp_i(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+__device__ __forceinline__ int sat_i32(double v) {
+    // cv::saturate_cast<int>(double) == cvRound (round-half-even) with saturation
+    if (!(v > -2147483648.0)) return (v != v) ? (int)0x80000000 : (int)0x80000000;
+    if (v >= 2147483647.0) return 0x7fffffff;
+    return __double2int_rn(v);
+}
+
+// OpenCV's in-place inversion of the forward 2x3 matrix (imgwarp.cpp; Appendix A step 1).
+__device__ __forceinline__ void invert_affine(const double* M, double* o) {
+    double m0 = M[0], m1 = M[1], m2 = M[2], m3 = M[3], m4 = M[4], m5 = M[5];
+    double D = __dsub_rn(__dmul_rn(m0, m4), __dmul_rn(m1, m3));
+    D = (D != 0.0) ? __ddiv_rn(1.0, D) : 0.0;
+    const double a11 = __dmul_rn(m4, D), a22 = __dmul_rn(m0, D);
+    m0 = a11; m1 = __dmul_rn(m1, -D); m3 = __dmul_rn(m3, -D); m4 = a22;
+    const double b1 = __dsub_rn(__dmul_rn(-m0, m2), __dmul_rn(m1, m5));
+    const double b2 = __dsub_rn(__dmul_rn(-m3, m2), __dmul_rn(m4, m5));
+    o[0] = m0; o[1] = m1; o[2] = b1; o[3] = m3; o[4] = m4; o[5] = b2;
+}
+
+// cv2's fixed-point coordinate terms for output column x / row y (Appendix A step 2)
+__device__ __forceinline__ int col_term(double m, int x) {
+    return clamp_i(sat_i32(__dmul_rn(__dmul_rn(m, (double)x), 1024.0)), -(1 << 30), 1 << 30);
+}
+__device__ __forceinline__ int row_term(double m, double b, int y) {
+    return clamp_i(sat_i32(__dmul_rn(__dadd_rn(__dmul_rn(m, (double)y), b), 1024.0)), -(1 << 30), 1 << 30) + 16;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace lh

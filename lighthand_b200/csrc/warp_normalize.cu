@@ -59,25 +59,6 @@ struct WarpParams {
     int vec_store;
 };
 
-__device__ __forceinline__ int sat_i32(double v) {
-    // cv::saturate_cast<int>(double) == cvRound (round-half-even) with saturation
-    if (!(v > -2147483648.0)) return (v != v) ? (int)0x80000000 : (int)0x80000000;
-    if (v >= 2147483647.0) return 0x7fffffff;
-    return __double2int_rn(v);
-}
-
-// OpenCV's in-place inversion of the forward 2x3 matrix (imgwarp.cpp; Appendix A step 1).
-__device__ __forceinline__ void invert_affine(const double* M, double* o) {
-    double m0 = M[0], m1 = M[1], m2 = M[2], m3 = M[3], m4 = M[4], m5 = M[5];
-    double D = __dsub_rn(__dmul_rn(m0, m4), __dmul_rn(m1, m3));
-    D = (D != 0.0) ? __ddiv_rn(1.0, D) : 0.0;
-    const double a11 = __dmul_rn(m4, D), a22 = __dmul_rn(m0, D);
-    m0 = a11; m1 = __dmul_rn(m1, -D); m3 = __dmul_rn(m3, -D); m4 = a22;
-    const double b1 = __dsub_rn(__dmul_rn(-m0, m2), __dmul_rn(m1, m5));
-    const double b2 = __dsub_rn(__dmul_rn(-m3, m2), __dmul_rn(m4, m5));
-    o[0] = m0; o[1] = m1; o[2] = b1; o[3] = m3; o[4] = m4; o[5] = b2;
-}
-
 __device__ __forceinline__ uint32_t lds32(const uint8_t* base, int word) {
     return reinterpret_cast<const uint32_t*>(base)[word];
 }
@@ -301,7 +282,6 @@ __global__ void __launch_bounds__(kWThreads) warp_cv2_kernel(const WarpParams p)
 #endif
 constexpr int kMaxPos = LH_FAST_MAXPOS;  // position records per CTA (3200 = 25 KB: a 32x32 tile rotated 45 degrees at unit scale is 62 x 49)
 
-__device__ __forceinline__ int clamp_i(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
 struct TileBox {       // footprint of one output tile in the source, in staged-record coordinates
     int lox, hix, loy, hiy;   // clamped tap-origin range (records -2 / sw and rows -2 / sh are all-zero)
@@ -326,14 +306,6 @@ __device__ __noinline__ uint4 taps_from_global(const uint8_t* img, int pitch_b, 
     }
     return make_uint4(__byte_perm(px[0], px[1], 0x5140), __byte_perm(px[0], px[1], 0x0062),
                       __byte_perm(px[2], px[3], 0x5140), __byte_perm(px[2], px[3], 0x0062));
-}
-
-// cv2's fixed-point coordinate terms for output column x / row y (Appendix A step 2), flip folded in
-__device__ __forceinline__ int col_term(double m, int x) {
-    return clamp_i(sat_i32(__dmul_rn(__dmul_rn(m, (double)x), 1024.0)), -(1 << 30), 1 << 30);
-}
-__device__ __forceinline__ int row_term(double m, double b, int y) {
-    return clamp_i(sat_i32(__dmul_rn(__dadd_rn(__dmul_rn(m, (double)y), b), 1024.0)), -(1 << 30), 1 << 30) + 16;
 }
 
 #ifndef LH_FAST_THREADS
@@ -582,7 +554,7 @@ __global__ void __launch_bounds__(kWThreads) resize_torch_kernel(const WarpParam
     const uint8_t* img = p.src + (long long)n * p.img_stride;
     const bool flip = p.flip ? (p.flip[n] != 0) : false;
     const float sy = __fdiv_rn((float)p.sh, (float)p.oh), sx = __fdiv_rn((float)p.sw, (float)p.ow);
-    float fy = __fsub_rn(__fmul_rn(sy, __fadd_rn((float)oy, 0.5f)), 0.5f);
+    float fy = fmaf(sy, __fadd_rn((float)oy, 0.5f), -0.5f);
     fy = fy < 0.f ? 0.f : fy;
     const int y0 = min((int)fy, p.sh - 1), y1 = min(y0 + 1, p.sh - 1);
     const float ly1 = fminf(fmaxf(__fsub_rn(fy, (float)y0), 0.f), 1.f), ly0 = __fsub_rn(1.0f, ly1);
@@ -591,7 +563,7 @@ __global__ void __launch_bounds__(kWThreads) resize_torch_kernel(const WarpParam
     float out[3][4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        float fx = __fsub_rn(__fmul_rn(sx, __fadd_rn((float)(ox + k), 0.5f)), 0.5f);
+        float fx = fmaf(sx, __fadd_rn((float)(ox + k), 0.5f), -0.5f);
         fx = fx < 0.f ? 0.f : fx;
         int x0 = min((int)fx, p.sw - 1), x1 = min(x0 + 1, p.sw - 1);
         const float lx1 = fminf(fmaxf(__fsub_rn(fx, (float)x0), 0.f), 1.f), lx0 = __fsub_rn(1.0f, lx1);
@@ -642,7 +614,7 @@ __global__ void __launch_bounds__(kFThreads, 8) resize_pairs_kernel(const WarpPa
     // torch: scale = in / out (float32); src = max(0, scale * (dst + 0.5) - 0.5); i0 = (int)src; lambda1 = src - i0
     const float sy = __fdiv_rn((float)p.sh, (float)p.oh), sx = __fdiv_rn((float)p.sw, (float)p.ow);
     auto src_index = [](float scale, int d) {
-        const float f = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)d, 0.5f)), 0.5f);
+        const float f = fmaf(scale, __fadd_rn((float)d, 0.5f), -0.5f);
         return f < 0.f ? 0.f : f;
     };
     const int cl = min(kTileW, p.ow - tx0) - 1, rl = min(kTileH, p.oh - ty0) - 1;

@@ -160,6 +160,69 @@ def warp_normalize(images_u8: torch.Tensor, fwd_affine: Optional[torch.Tensor], 
 
 
 # ---------------------------------------------------------------------------------------------
+# FreiHAND image path (a-3)
+# ---------------------------------------------------------------------------------------------
+
+def frei_rgb_processing(images_u8: torch.Tensor, desc: torch.Tensor, res: int, scratch_floats: int,
+                        max_rot_px: int, out: Optional[torch.Tensor] = None,
+                        rot_index: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """rgb_processing (src/datasets/frei_dataloader.py:134-147) of a batch.  images_u8 [N,H,W,3] uint8 CUDA;
+    ``desc`` = uint8 CUDA tensor holding N packed ``lh_frei_desc`` records (utils.image_ops.crop_descriptors);
+    returns float32 [N,3,res,res] in 0..1."""
+    require_cuda()
+    lib = _lib.load()
+    images_u8 = _dev(images_u8, torch.uint8, "images")
+    if images_u8.dim() != 4 or images_u8.shape[3] != 3:
+        raise LighthandError("images: expected [N,H,W,3] uint8")
+    n, sh, sw, _ = images_u8.shape
+    desc = _dev(desc, torch.uint8, "desc")
+    if desc.numel() != n * C.sizeof(_lib.FreiDesc):
+        raise LighthandError("desc: expected N packed lh_frei_desc records")
+    if out is None:
+        out = torch.empty((n, 3, res, res), dtype=torch.float32, device=images_u8.device)
+    else:
+        out = _dev(out, torch.float32, "out")
+        if tuple(out.shape) != (n, 3, res, res):
+            raise LighthandError("out: wrong shape")
+    if n == 0:
+        return out
+    scratch = torch.empty(int(scratch_floats), dtype=torch.float32, device=images_u8.device) if max_rot_px > 0 else None
+    if rot_index is not None:
+        rot_index = _dev(rot_index, torch.int32, "rot_index")
+    with torch.cuda.device(images_u8.device):
+        check(lib.lh_frei_rgb_processing(images_u8.data_ptr(), sh * sw * 3, sh, sw, sw * 3, desc.data_ptr(), n, int(res),
+                                         _ptr(rot_index), 0 if rot_index is None else rot_index.numel(),
+                                         _ptr(scratch), int(max_rot_px), out.data_ptr(), _stream()),
+              "lh_frei_rgb_processing")
+    return out
+
+
+def resize_normalize_f32(src: torch.Tensor, out_hw: Sequence[int], mean=IMAGENET_MEAN, std=IMAGENET_STD,
+                         chan_order: int = LH_CHAN_RGB, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """transforms.Resize(out_hw) on a float CHW batch + Normalize (+ channel reversal): src [N,3,h,w] float32 CUDA
+    -> [N,3,oh,ow] (src/datasets/frei_dataloader.py:279-283,338).  mean=None skips the normalisation."""
+    require_cuda()
+    lib = _lib.load()
+    src = _dev(src, torch.float32, "src")
+    if src.dim() != 4 or src.shape[1] != 3:
+        raise LighthandError("src: expected [N,3,H,W] float32")
+    n, _, sh, sw = src.shape
+    oh, ow = int(out_hw[0]), int(out_hw[1])
+    if out is None:
+        out = torch.empty((n, 3, oh, ow), dtype=torch.float32, device=src.device)
+    else:
+        out = _dev(out, torch.float32, "out")
+        if tuple(out.shape) != (n, 3, oh, ow):
+            raise LighthandError("out: wrong shape")
+    if n == 0:
+        return out
+    with torch.cuda.device(src.device):
+        check(lib.lh_resize_normalize_f32(src.data_ptr(), n, sh, sw, _mean_std(mean, std), chan_order, out.data_ptr(),
+                                          oh, ow, _stream()), "lh_resize_normalize_f32")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # K2
 # ---------------------------------------------------------------------------------------------
 

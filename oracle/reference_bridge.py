@@ -114,5 +114,7 @@ def load():
     ns.crop = _io.crop
     ns.transform = _io.transform
     ns.get_transform = _io.get_transform
+    from src.datasets import frei_dataloader as _frei
+    ns.HandMeshTSVDataset = _frei.HandMeshTSVDataset
     _loaded = ns
     return ns

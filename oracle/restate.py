@@ -198,7 +198,10 @@ def resize_bilinear_model(chw_f32, out_h, out_w):
     def axis(insz, outsz):
         scale = f(insz) / f(outsz)
         d = np.arange(outsz, dtype=f)
-        s = np.maximum(scale * (d + f(0.5)) - f(0.5), f(0)).astype(f)
+        # ATen evaluates scale * (dst + 0.5) - 0.5 as ONE fused multiply-add (float32); emulated through float64,
+        # where the product of two float32 values is exact
+        s = (np.float64(scale) * (d + f(0.5)).astype(np.float64) - 0.5).astype(f)
+        s = np.maximum(s, f(0)).astype(f)
         i0 = np.minimum(s.astype(np.int64), insz - 1)
         i1 = np.minimum(i0 + 1, insz - 1)
         l1 = np.clip(s - i0.astype(f), f(0), f(1)).astype(f)
@@ -222,6 +225,166 @@ def resize_normalize_sample(img_u8, out_hw, mean=IMAGENET_MEAN, std=IMAGENET_STD
     m = torch.tensor(mean, dtype=torch.float32).view(-1, 1, 1)
     s = torch.tensor(std, dtype=torch.float32).view(-1, 1, 1)
     return ((t - m) / s).numpy()
+
+
+# ----------------------------------------------------------------------------
+# a-3  FreiHAND multi-stage crop  (src/utils/image_ops.py:25-131,
+#      src/datasets/frei_dataloader.py:134-160,276-338)
+# ----------------------------------------------------------------------------
+FREI_RES = 224      # HandMeshTSVDataset.img_res (frei_dataloader.py:75)
+FREI_OUT = 256      # the Resize after rgb_processing (frei_dataloader.py:279-280)
+
+
+def frei_get_transform(center, scale, res, rot=0):
+    """src/utils/image_ops.py:59-83."""
+    h = 200 * scale
+    t = np.zeros((3, 3))
+    t[0, 0] = float(res[1]) / h
+    t[1, 1] = float(res[0]) / h
+    t[0, 2] = res[1] * (-float(center[0]) / h + .5)
+    t[1, 2] = res[0] * (-float(center[1]) / h + .5)
+    t[2, 2] = 1
+    if not rot == 0:
+        rot = -rot
+        rot_mat = np.zeros((3, 3))
+        rot_rad = rot * np.pi / 180
+        sn, cs = np.sin(rot_rad), np.cos(rot_rad)
+        rot_mat[0, :2] = [cs, -sn]
+        rot_mat[1, :2] = [sn, cs]
+        rot_mat[2, 2] = 1
+        t_mat = np.eye(3)
+        t_mat[0, 2] = -res[1] / 2
+        t_mat[1, 2] = -res[0] / 2
+        t_inv = t_mat.copy()
+        t_inv[:2, 2] *= -1
+        t = np.dot(t_inv, np.dot(rot_mat, np.dot(t_mat, t)))
+    return t
+
+
+def frei_transform(pt, center, scale, res, invert=0, rot=0):
+    """src/utils/image_ops.py:85-95 -- the inverse goes through torch.inverse (float64) and the
+    result is truncated toward zero."""
+    t = frei_get_transform(center, scale, res, rot=rot)
+    if invert:
+        t = torch.inverse(torch.from_numpy(t)).numpy()
+    new_pt = np.array([pt[0] - 1, pt[1] - 1, 1.]).T
+    new_pt = np.dot(t, new_pt)
+    return new_pt[:2].astype(int) + 1
+
+
+def frei_crop_geometry(center, scale, res, rot, img_hw):
+    """The integer bookkeeping of ``crop`` (src/utils/image_ops.py:99-121): window corners in the
+    source (after the rotation padding), the padding, and the copy ranges."""
+    ul = np.array(frei_transform([1, 1], center, scale, res, invert=1)) - 1
+    br = np.array(frei_transform([res[0] + 1, res[1] + 1], center, scale, res, invert=1)) - 1
+    pad = int(np.linalg.norm(br - ul) / 2 - float(br[1] - ul[1]) / 2)
+    if not rot == 0:
+        ul = ul - pad
+        br = br + pad
+    ih, iw = img_hw
+    return dict(ul=ul, br=br, pad=pad, shape=(int(br[1] - ul[1]), int(br[0] - ul[0])),
+                new_x=(max(0, -ul[0]), min(br[0], iw) - ul[0]), new_y=(max(0, -ul[1]), min(br[1], ih) - ul[1]),
+                old_x=(max(0, ul[0]), min(iw, br[0])), old_y=(max(0, ul[1]), min(ih, br[1])))
+
+
+def cv2_rotation_matrix(center, angle, scale=1.0):
+    """Model of cv2.getRotationMatrix2D (OpenCV imgwarp.cpp; call site src/utils/image_ops.py:33):
+    the centre is a Point2f (float32), the trigonometry is double."""
+    cx, cy = float(np.float32(center[0])), float(np.float32(center[1]))
+    a = angle * np.pi / 180
+    alpha, beta = np.cos(a) * scale, np.sin(a) * scale
+    return np.array([[alpha, beta, (1 - alpha) * cx - beta * cy],
+                     [-beta, alpha, beta * cx + (1 - alpha) * cy]], dtype=np.float64)
+
+
+def cv2_resize_linear_model(img, out_w, out_h):
+    """Numpy model of cv2.resize(img_float64, (out_w, out_h), INTER_LINEAR) as the installed OpenCV (4.13)
+    computes it for CV_64F (call site src/utils/image_ops.py:49): half-pixel source coordinates, edge clamp,
+    weights and accumulation in double -- rows first, then columns.  (Agrees with cv2 to 2e-11 on 0..255
+    data; a float32-weight variant, which older OpenCV builds use, differs from it by <= 0.005, far inside
+    the 1-LSB bar of this path.)"""
+    img = np.asarray(img, dtype=np.float64)
+    sh, sw = img.shape[:2]
+
+    def axis(ssize, dsize):
+        scale = 1.0 / (float(dsize) / float(ssize))
+        f = (np.arange(dsize, dtype=np.float64) + 0.5) * scale - 0.5
+        s = np.floor(f).astype(np.int64)
+        f = f - s
+        lo = s < 0
+        f[lo] = 0
+        s[lo] = 0
+        hi = s >= ssize - 1
+        f[hi] = 0
+        s[hi] = ssize - 1
+        return s, np.minimum(s + 1, ssize - 1), 1.0 - f, f
+
+    x0, x1, a0, a1 = axis(sw, out_w)
+    y0, y1, b0, b1 = axis(sh, out_h)
+    rows = img[:, x0] * a0[None, :, None] + img[:, x1] * a1[None, :, None]
+    return rows[y0] * b0[:, None, None] + rows[y1] * b1[:, None, None]
+
+
+def frei_crop(img, center, scale, res, rot=0, model=False):
+    """src/utils/image_ops.py:97-131: window copy into a zero float64 canvas, optional rotation about
+    the canvas centre (``myimrotate`` :25-44) with the rotation padding removed, cv2.resize to ``res``.
+    model=False calls the installed cv2 exactly as the reference does; model=True uses the numpy models
+    above (what the CUDA kernels implement)."""
+    g = frei_crop_geometry(center, scale, res, rot, img.shape[:2])
+    shape = list(g["shape"]) + ([img.shape[2]] if img.ndim > 2 else [])
+    new_img = np.zeros(shape)
+    (nx0, nx1), (ny0, ny1), (ox0, ox1), (oy0, oy1) = g["new_x"], g["new_y"], g["old_x"], g["old_y"]
+    new_img[ny0:ny1, nx0:nx1] = img[oy0:oy1, ox0:ox1]
+    if not rot == 0:
+        h, w = new_img.shape[:2]
+        centre = ((w - 1) * 0.5, (h - 1) * 0.5)
+        pad = g["pad"]
+        if model:
+            new_img = warp_affine_model(new_img.astype(np.float32), cv2_rotation_matrix(centre, rot), h, w).astype(np.float64)
+        else:
+            new_img = cv2.warpAffine(new_img, cv2.getRotationMatrix2D(centre, rot, 1.0), (w, h), borderValue=0)
+        new_img = new_img[pad:-pad, pad:-pad]
+    if model:
+        return cv2_resize_linear_model(new_img, res[0], res[1])
+    return cv2.resize(new_img, (res[0], res[1]), interpolation=cv2.INTER_LINEAR)
+
+
+def frei_rgb_processing(img, center, scale, rot, pn, res=FREI_RES, model=False):
+    """src/datasets/frei_dataloader.py:134-147 with flip = 0 (:107): crop, per-channel pixel noise with
+    clip to 0..255 (float64), CHW float32 / 255."""
+    rgb = frei_crop(img, center, scale, [res, res], rot=rot, model=model)
+    for c in range(3):
+        rgb[:, :, c] = np.minimum(255.0, np.maximum(0.0, rgb[:, :, c] * pn[c]))
+    return np.transpose(rgb.astype("float32"), (2, 0, 1)) / 255.0
+
+
+def frei_image(img, center, scale, rot, pn, model=False, mean=IMAGENET_MEAN, std=IMAGENET_STD, res=FREI_RES,
+               out=FREI_OUT):
+    """The image HandMeshTSVDataset.__getitem__ returns (src/datasets/frei_dataloader.py:276-283,338):
+    rgb_processing -> Resize((256,256)) on the float tensor (torchvision 0.12: no antialias) -> Normalize ->
+    channels (2,1,0)."""
+    t = torch.from_numpy(frei_rgb_processing(img, center, scale, rot, pn, res=res, model=model)).float()
+    t = torch.nn.functional.interpolate(t[None], size=(out, out), mode="bilinear",
+                                        align_corners=False, antialias=False)[0]
+    m = torch.tensor(mean, dtype=torch.float32).view(-1, 1, 1)
+    s = torch.tensor(std, dtype=torch.float32).view(-1, 1, 1)
+    return ((t - m) / s)[(2, 1, 0), :, :].numpy()
+
+
+def frei_j2d_processing(kp, center, scale, r, res=FREI_RES):
+    """src/datasets/frei_dataloader.py:148-160 with f = 0: every keypoint through ``transform`` (integer
+    truncation), then normalised to [-1, 1]."""
+    kp = np.array(kp, dtype=np.float64)
+    for i in range(kp.shape[0]):
+        kp[i, 0:2] = frei_transform(kp[i, 0:2] + 1, center, scale, [res, res], rot=r)
+    kp[:, :-1] = 2. * kp[:, :-1] / res - 1.
+    return kp.astype("float32")
+
+
+def frei_joint_2d(kp, center, scale, r):
+    """src/datasets/frei_dataloader.py:334-335: the 2-D joints the heat-maps are drawn from."""
+    j = torch.from_numpy(frei_j2d_processing(kp, center, scale, r)).float()
+    return ((j[:, :-1] * 100 + 112) * (FREI_OUT / FREI_RES)).numpy()
 
 
 # ----------------------------------------------------------------------------

@@ -238,6 +238,42 @@ def make_resize():
     save("resize.npz", imgs=imgs, out=out, out_80x72=out2)
 
 
+def make_frei(ns):
+    """HandMeshTSVDataset.rgb_processing / j2d_processing (src/datasets/frei_dataloader.py:134-160) and the tail
+    of __getitem__ (:276-283, 334-338: Resize, Normalize, channels (2,1,0), joint rescale), called unbound on a
+    stand-in ``self``.  Small geometry (img_res 56 -> 64) keeps the fixture small; crop() itself is also stored at
+    the real 224 geometry for one rotated sample."""
+    from torchvision import transforms
+    rng = np.random.default_rng(18)
+    ds = ns.HandMeshTSVDataset
+    stub = types.SimpleNamespace(img_res=56)
+    norm = transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])
+    n = 8
+    imgs = rng.integers(0, 256, (n, 64, 64, 3), dtype=np.uint8)
+    centers = 32 + rng.uniform(-8, 8, (n, 2))
+    scales = rng.uniform(0.2, 0.4, n)
+    rots = np.where(np.arange(n) % 2 == 0, 0.0, np.clip(rng.standard_normal(n) * 90, -180, 180))
+    rots[1] = 90.0
+    pns = rng.uniform(0.6, 1.4, (n, 3))
+    kps = np.concatenate([rng.uniform(0, 64, (n, 21, 2)), np.ones((n, 21, 1))], axis=2)
+    rgb, final, j2d, joint_2d = [], [], [], []
+    for i in range(n):
+        a = ds.rgb_processing(stub, imgs[i], centers[i], scales[i], rots[i], 0, pns[i])
+        rgb.append(a)
+        t = transforms.Resize((64, 64))(torch.from_numpy(a).float())
+        final.append(norm(t)[(2, 1, 0), :, :].numpy())
+        k = ds.j2d_processing(stub, kps[i].copy(), centers[i], scales[i], rots[i], 0)
+        j2d.append(k)
+        joint_2d.append(((torch.from_numpy(k).float()[:, :-1] * 100 + 112) * (256 / 224)).numpy())
+    big = rng.integers(0, 256, (1, 224, 224, 3), dtype=np.uint8)
+    big_par = np.array([[120.25, 100.0, 1.1, -37.5]])      # cx, cy, scale, rot
+    crops = [ns.crop(big[i], big_par[i, :2], big_par[i, 2], [224, 224], rot=big_par[i, 3]).astype(np.float32)
+             for i in range(1)]
+    save("frei.npz", imgs=imgs, centers=centers, scales=scales, rots=rots, pns=pns, kps=kps, rgb=np.stack(rgb),
+         final=np.stack(final), j2d=np.stack(j2d), joint_2d=np.stack(joint_2d), big=big, big_par=big_par,
+         crops=np.stack(crops))
+
+
 def main():
     if not rb.available():
         raise SystemExit("reference tree not mounted; fixtures can only be generated in the build container")
@@ -249,6 +285,7 @@ def main():
     make_eval(ns)
     make_warp(ns)
     make_resize()
+    make_frei(ns)
     import cv2
     import torchvision
     with open(os.path.join(HERE, "VERSIONS.json"), "w") as f:

@@ -99,3 +99,35 @@ def test_metric_allreduce_gloo_world2(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=180)
         assert p.returncode == 0, out.decode()[-2000:]
+
+
+def test_frei_crop_descriptors_follow_the_reference_bookkeeping():
+    """utils.image_ops.crop_descriptors == the integer window arithmetic of crop() (oracle.frei_crop_geometry),
+    and the packed record has the layout include/lighthand_b200.h declares."""
+    import ctypes
+    from lighthand_b200 import _lib
+    from lighthand_b200.utils import image_ops
+    from oracle import restate as R
+    assert ctypes.sizeof(_lib.FreiDesc) == 112 and _lib.FreiDesc.iM.offset == 24 and _lib.FreiDesc.scratch_off.offset == 104
+    rng = np.random.default_rng(21)
+    n = 40
+    centers = 112 + rng.uniform(-80, 80, (n, 2))
+    scales = rng.uniform(0.4, 1.8, n)
+    rots = np.where(rng.uniform(size=n) < 0.5, 0.0, rng.uniform(-180, 180, n))
+    pns = rng.uniform(0.6, 1.4, (n, 3))
+    recs, scratch, max_px = image_ops.crop_descriptors(centers, scales, [224, 224], rots, pns)
+    off = 0
+    for i in range(n):
+        g = R.frei_crop_geometry(centers[i], float(scales[i]), [224, 224], float(rots[i]), (224, 224))
+        r = recs[i]
+        assert (r.ulx, r.uly) == (int(g["ul"][0]), int(g["ul"][1])) and (r.ch, r.cw) == g["shape"]
+        assert r.pad == g["pad"] and r.rotated == int(rots[i] != 0)
+        assert np.allclose([r.pn[0], r.pn[1], r.pn[2]], pns[i].astype(np.float32))
+        if r.rotated:
+            want = R.cv2_invert_affine(R.cv2_rotation_matrix(((r.cw - 1) * 0.5, (r.ch - 1) * 0.5), float(rots[i]))).ravel()
+            assert np.array_equal(np.array(list(r.iM)), want) and r.scratch_off == off
+            off += 3 * (r.cw - 2 * r.pad) * (r.ch - 2 * r.pad)
+    assert scratch == off and max_px > 0
+    for pt in ([1, 1], [100.5, 30.25]):
+        assert np.array_equal(image_ops.transform(pt, centers[0], scales[0], [224, 224], invert=1, rot=rots[1]),
+                              R.frei_transform(pt, centers[0], scales[0], [224, 224], invert=1, rot=rots[1]))

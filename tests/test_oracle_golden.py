@@ -162,3 +162,38 @@ def test_resize_normalize_matches_torchvision_compose():
         m = np.array(R.IMAGENET_MEAN, np.float32)[:, None, None]
         s = np.array(R.IMAGENET_STD, np.float32)[:, None, None]
         np.testing.assert_allclose((model - m) / s, want, rtol=1e-5, atol=1e-5)
+
+
+def test_frei_path_matches_reference():
+    """a-3: rgb_processing / j2d_processing / the __getitem__ tail, through cv2 like the reference (tolerance 0
+    for the float64 cv2 stages) and through the numpy models the CUDA kernels implement."""
+    g = golden("frei.npz")
+    for i in range(len(g["imgs"])):
+        args = (g["imgs"][i], g["centers"][i], float(g["scales"][i]), float(g["rots"][i]), g["pns"][i])
+        assert np.array_equal(R.frei_rgb_processing(*args, res=56), g["rgb"][i])
+        np.testing.assert_allclose(R.frei_rgb_processing(*args, res=56, model=True), g["rgb"][i], rtol=0, atol=1e-7)
+        # Resize: torchvision 0.26 routes through its antialias kernel (same weights when up-sampling, ~1 ulp apart)
+        np.testing.assert_allclose(R.frei_image(*args, res=56, out=64), g["final"][i], rtol=1e-5, atol=1e-5)
+        kp = R.frei_j2d_processing(g["kps"][i], g["centers"][i], float(g["scales"][i]), float(g["rots"][i]), res=56)
+        assert np.array_equal(kp, g["j2d"][i])
+    par = g["big_par"][0]
+    for model in (False, True):
+        c = R.frei_crop(g["big"][0], par[:2], float(par[2]), [224, 224], rot=float(par[3]), model=model)
+        np.testing.assert_allclose(c.astype(np.float32), g["crops"][0], rtol=0, atol=0 if not model else 1e-4)
+
+
+def test_cv2_models_of_the_frei_stages():
+    """The numpy models of cv2.getRotationMatrix2D / warpAffine(float64) / resize(float64) against the installed cv2."""
+    import cv2
+    rng = np.random.default_rng(5)
+    for _ in range(6):
+        sh, sw = int(rng.integers(40, 120)), int(rng.integers(40, 120))
+        img = rng.integers(0, 256, (sh, sw, 3)).astype(np.float64)
+        ang = float(rng.uniform(-180, 180))
+        c = ((sw - 1) * 0.5, (sh - 1) * 0.5)
+        M = R.cv2_rotation_matrix(c, ang)
+        np.testing.assert_allclose(M, cv2.getRotationMatrix2D(c, ang, 1.0), rtol=0, atol=1e-12)
+        a = cv2.warpAffine(img, cv2.getRotationMatrix2D(c, ang, 1.0), (sw, sh), borderValue=0)
+        assert np.array_equal(R.warp_affine_model(img.astype(np.float32), M, sh, sw).astype(np.float64), a)
+        np.testing.assert_allclose(R.cv2_resize_linear_model(img, 56, 56),
+                                   cv2.resize(img, (56, 56), interpolation=cv2.INTER_LINEAR), rtol=0, atol=1e-9)

@@ -66,3 +66,31 @@ def test_patch_random(ref):
         b, t2, it2 = ref.generate_patch_image(img, bbox, flip, scale, rot, (64, 48))
         assert np.array_equal(t, t2) and np.array_equal(it, it2) and np.array_equal(a, b)
         assert np.array_equal(R.warp_affine_model(img, t, 64, 48, flip=flip).astype(np.float32), b)
+
+
+def test_frei_crop_and_dataset_tail_random(ref):
+    """a-3 live: crop / rgb_processing / j2d_processing of the reference on random windows (inside, partly and
+    mostly outside the image; rotated or not)."""
+    import types
+    stub = types.SimpleNamespace(img_res=224)
+    ds = ref.HandMeshTSVDataset
+    rng = np.random.default_rng(106)
+    for it in range(14):
+        h, w = (224, 224) if it % 2 else (int(rng.integers(150, 300)), int(rng.integers(150, 300)))
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        center = [w / 2 + rng.uniform(-60, 60), h / 2 + rng.uniform(-60, 60)]
+        scale = float(rng.uniform(0.5, 1.6))
+        rot = 0 if it % 3 == 0 else float(np.clip(rng.standard_normal() * 90, -180, 180))
+        pn = rng.uniform(0.6, 1.4, 3)
+        a = ref.crop(img, center, scale, [224, 224], rot=rot)
+        assert np.array_equal(R.frei_crop(img, center, scale, [224, 224], rot=rot), a)
+        np.testing.assert_allclose(R.frei_crop(img, center, scale, [224, 224], rot=rot, model=True), a, rtol=0, atol=1e-9)
+        assert np.array_equal(R.frei_rgb_processing(img, center, scale, rot, pn),
+                              ds.rgb_processing(stub, img, center, scale, rot, 0, pn))
+        kp = np.concatenate([rng.uniform(-20, 260, (21, 2)), np.ones((21, 1))], axis=1)
+        assert np.array_equal(R.frei_j2d_processing(kp, center, scale, rot),
+                              ds.j2d_processing(stub, kp.copy(), center, scale, rot, 0))
+        for pt in ([1, 1], [225, 225], [17.5, 90.25]):
+            for inv in (0, 1):
+                assert np.array_equal(R.frei_transform(pt, center, scale, [224, 224], invert=inv, rot=rot),
+                                      ref.transform(pt, center, scale, [224, 224], invert=inv, rot=rot))

@@ -76,6 +76,28 @@ def main():
     lut = ops.build_norm_lut(device=dev)
     rec("warp rot+scale lut", timeit(lambda i: ops.warp_normalize(imgs[i], M, (S, S), out=out_img, lut=lut), R), k1_bytes)
     rec("resize torch-mode", timeit(lambda i: ops.warp_normalize(imgs[i], None, (S, S), out=out_img, interp=ops.LH_INTERP_TORCH), R), k1_bytes)
+    # FreiHAND image path (a-3): 224x224 sources, train-time augmentation mix (40 % rotated), 224 -> 256
+    import numpy as np
+    from lighthand_b200.datasets import frei_dataloader as F
+    from lighthand_b200.utils import image_ops
+    rng = np.random.RandomState(0)
+    fimgs = [torch.randint(0, 256, (N, 224, 224, 3), device=dev, dtype=torch.uint8, generator=g) for _ in range(R)]
+    augm = [F.augm_params(True, rng) for _ in range(N)]
+    centers = 112 + rng.uniform(-10, 10, (N, 2))
+    recs, sfl, mpx = image_ops.crop_descriptors(centers, [a[3] for a in augm], [224, 224], [a[2] for a in augm], [a[1] for a in augm])
+    desc = image_ops.descriptors_to_device(recs, dev)
+    rgb = torch.empty((N, 3, 224, 224), device=dev)
+    lib = ops._lib.load()
+    scratch = torch.empty(max(sfl, 1), device=dev)
+    rot = torch.tensor([i for i, r in enumerate(recs) if r.rotated], dtype=torch.int32, device=dev)
+    def frei_rgb(i):
+        ops.check(lib.lh_frei_rgb_processing(fimgs[i].data_ptr(), 224 * 224 * 3, 224, 224, 224 * 3, desc.data_ptr(), N, 224,
+                                             rot.data_ptr(), rot.numel(), scratch.data_ptr(), mpx, rgb.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream))
+    frei_bytes = N * (224 * 224 * 3 + 224 * 224 * 12)
+    rec("frei rgb_processing (rotate+resize)", timeit(frei_rgb, R), frei_bytes)
+    rec("frei Resize+Normalize+BGR f32", timeit(lambda i: ops.resize_normalize_f32(rgb, (S, S), chan_order=ops.LH_CHAN_BGR, out=out_img), R),
+        N * (224 * 224 * 12 + S * S * 12))
     big_src = torch.empty((N, 3, S, S), device=dev)
     rec("torch_copy_201MB", timeit(lambda i: out_img.copy_(big_src), 1), 2 * N * 3 * S * S * 4)
     print(json.dumps(res, indent=1))
