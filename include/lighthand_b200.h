@@ -233,6 +233,25 @@ int lh_resize_normalize_f32(const float* src, int N, int src_h, int src_w, const
                             float* dst, int out_h, int out_w, lh_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * ColorJitter + Normalize on float CHW images in 0..1 (SURVEY 8 a-2 augmentation branch / f-2).
+ * Replaces transforms.ColorJitter(0.5,0.5,0.5,0.5) -> transforms.Normalize  src/tools/dataset.py:139-145
+ * (torchvision's tensor implementation: _blend, rgb_to_grayscale, _rgb2hsv/_hsv2rgb, same float32 operation order).
+ * RNG contract: the draw stays on the host in torchvision's order (torch.randperm(4), then uniform draws for
+ * brightness, contrast, saturation, hue: lighthand_b200/tools/dataset.py color_jitter_params); the device applies it.
+ * ------------------------------------------------------------------------------------------ */
+#define LH_JITTER_PARTS 32   /* partial sums per image of the contrast step's mean grey level */
+typedef struct lh_jitter_params {
+    int32_t order[4];       /* torchvision fn ids in application order: 0 brightness 1 contrast 2 saturation 3 hue; -1 skips */
+    float factor[4];        /* indexed by fn id: brightness, contrast, saturation factors; hue shift in [-0.5, 0.5]            */
+    float one_minus[4];     /* float(1.0 - factor) as Python computes it (double subtraction, then float32); unused for hue    */
+    int32_t apply;          /* 0: this image is only normalised (idx >= len * ratio_of_aug, src/tools/dataset.py:134)          */
+} lh_jitter_params;
+/* src dev [N,3,H,W]; params dev [N]; mean_std host [6] or NULL; dst dev [N,3,H,W] (may alias src);
+ * ws dev double [N * LH_JITTER_PARTS]. */
+int lh_color_jitter_normalize(const float* src, const lh_jitter_params* params, int N, int H, int W,
+                              const float* mean_std, float* dst, double* ws, lh_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Host-buffer pipeline context (what a non-torch host binds; also the e2e benchmark path).
  * Owns device buffers, pinned staging and two streams; one step is
  *   H2D -> K1 -> fused(K2,K3,K4,K5) -> D2H   (two kernel launches).

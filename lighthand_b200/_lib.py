@@ -65,6 +65,12 @@ class FreiDesc(C.Structure):
     ]
 
 
+class JitterParams(C.Structure):
+    _fields_ = [("order", C.c_int32 * 4), ("factor", c_f * 4), ("one_minus", c_f * 4), ("apply", C.c_int32)]
+
+
+LH_JITTER_PARTS = 32
+
 # name -> (restype, argtypes); every symbol include/lighthand_b200.h declares
 PROTOTYPES = {
     "lh_abi_version": (c_i, []),
@@ -83,6 +89,7 @@ PROTOTYPES = {
                                  c_p, c_p, c_p, c_p, c_p]),
     "lh_frei_rgb_processing": (c_i, [c_p, c_i64, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_i, c_p, c_i64, c_p, c_p]),
     "lh_resize_normalize_f32": (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, c_p, c_i, c_i, c_p]),
+    "lh_color_jitter_normalize": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "lh_pipeline_create": (c_i, [C.POINTER(PipelineCfg), c_p, c_i, C.POINTER(c_p)]),
     "lh_pipeline_destroy": (None, [c_p]),
     "lh_pipeline_input_dev": (c_p, [c_p]),

@@ -222,6 +222,36 @@ def resize_normalize_f32(src: torch.Tensor, out_hw: Sequence[int], mean=IMAGENET
     return out
 
 
+def color_jitter_normalize(images: torch.Tensor, params, mean=IMAGENET_MEAN, std=IMAGENET_STD,
+                           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """transforms.ColorJitter -> transforms.Normalize (src/tools/dataset.py:139-145) on float CHW images in 0..1.
+    images [N,3,H,W] float32 CUDA; ``params`` = ctypes array of N ``lh_jitter_params``
+    (tools.dataset.color_jitter_params); ``out`` may be ``images`` itself.  mean=None skips the normalisation."""
+    require_cuda()
+    lib = _lib.load()
+    images = _dev(images, torch.float32, "images")
+    if images.dim() != 4 or images.shape[1] != 3:
+        raise LighthandError("images: expected [N,3,H,W] float32")
+    n, _, h, w = images.shape
+    if len(params) != n:
+        raise LighthandError("params: expected one lh_jitter_params per image")
+    if out is None:
+        out = torch.empty_like(images)
+    else:
+        out = _dev(out, torch.float32, "out")
+        if tuple(out.shape) != tuple(images.shape):
+            raise LighthandError("out: wrong shape")
+    if n == 0:
+        return out
+    raw = np.frombuffer(bytes(params), dtype=np.uint8).copy()
+    d_params = torch.from_numpy(raw).to(images.device)
+    ws = torch.empty(n * _lib.LH_JITTER_PARTS, dtype=torch.float64, device=images.device)
+    with torch.cuda.device(images.device):
+        check(lib.lh_color_jitter_normalize(images.data_ptr(), d_params.data_ptr(), n, h, w, _mean_std(mean, std),
+                                            out.data_ptr(), ws.data_ptr(), _stream()), "lh_color_jitter_normalize")
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # K2
 # ---------------------------------------------------------------------------------------------

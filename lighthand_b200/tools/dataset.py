@@ -35,16 +35,47 @@ def generate_target(joints, num_joints=21, heatmap_size=(64, 64), feat_stride=(4
     return (target, weight) if return_weight else target
 
 
+def color_jitter_params(apply_flags, brightness=0.5, contrast=0.5, saturation=0.5, hue=0.5):
+    """Host half of ``transforms.ColorJitter(brightness, contrast, saturation, hue)`` (src/tools/dataset.py:139-141)
+    for a batch: for every sample with a true flag, the draw torchvision's ``ColorJitter.get_params`` makes --
+    ``torch.randperm(4)``, then one ``uniform_`` each for brightness, contrast, saturation, hue, from torch's default
+    generator -- so a seeded run reproduces the reference's stream sample by sample.  Returns a ctypes array of
+    ``lh_jitter_params``."""
+    from .. import _lib
+    n = len(apply_flags)
+    recs = (_lib.JitterParams * n)()
+    ranges = [(max(0.0, 1 - brightness), 1 + brightness), (max(0.0, 1 - contrast), 1 + contrast),
+              (max(0.0, 1 - saturation), 1 + saturation), (-hue, hue)]
+    for i, flag in enumerate(apply_flags):
+        r = recs[i]
+        r.apply = int(bool(flag))
+        for k in range(4):
+            r.order[k] = -1
+        if not flag:
+            continue
+        fn_idx = torch.randperm(4)
+        fac = [float(torch.empty(1).uniform_(lo, hi)) for lo, hi in ranges]
+        for k in range(4):
+            r.order[k] = int(fn_idx[k])
+            r.factor[k] = fac[k]
+            r.one_minus[k] = 1.0 - fac[k]
+    return recs
+
+
 class GpuCollate:
     """collate_fn for a DataLoader whose dataset yields ``(image_u8_hwc, joint_2d)``:
     returns ``(images f32[N,3,S,S], joint_2d f32[N,J,2], heatmaps f32[N,J,H,W])`` on ``device`` --
     the triple the reference's loops consume (src/utils/method.py:160).  Keypoints are scaled by
-    S / S_src (src/tools/dataset.py:132)."""
+    S / S_src (src/tools/dataset.py:132).  A dataset that yields a third element per sample,
+    ``(image, joint_2d, augment)``, gets ``ColorJitter(0.5, 0.5, 0.5, 0.5)`` on the samples whose flag is true
+    (the reference's ``idx < len(meta) * ratio_of_aug``, src/tools/dataset.py:134-146), drawn per sample from
+    torch's generator in torchvision's order."""
 
     def __init__(self, image_size=256, heatmap_size=64, sigma=2, device="cuda",
-                 mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD):
+                 mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD, jitter=(0.5, 0.5, 0.5, 0.5)):
         self.image_size, self.heatmap_size, self.sigma = image_size, heatmap_size, sigma
         self.device, self.mean, self.std = torch.device(device), mean, std
+        self.jitter = jitter
 
     def __call__(self, samples):
         imgs = np.stack([np.asarray(s[0], dtype=np.uint8) for s in samples])
@@ -53,8 +84,16 @@ class GpuCollate:
         joints = joints * (self.image_size / src)
         d_imgs = torch.from_numpy(imgs).to(self.device, non_blocking=True)
         d_joints = joints.to(self.device, non_blocking=True)
-        images = ops.warp_normalize(d_imgs, None, (self.image_size, self.image_size), mean=self.mean,
-                                    std=self.std, interp=ops.LH_INTERP_TORCH)
+        flags = [bool(s[2]) for s in samples] if samples and len(samples[0]) > 2 else None
+        if flags is not None and any(flags):
+            # ToTensor -> Resize, then ColorJitter -> Normalize in one more pass
+            images = ops.warp_normalize(d_imgs, None, (self.image_size, self.image_size), mean=None, std=None,
+                                        interp=ops.LH_INTERP_TORCH)
+            images = ops.color_jitter_normalize(images, color_jitter_params(flags, *self.jitter), self.mean, self.std,
+                                                out=images)
+        else:
+            images = ops.warp_normalize(d_imgs, None, (self.image_size, self.image_size), mean=self.mean,
+                                        std=self.std, interp=ops.LH_INTERP_TORCH)
         stride = self.image_size / self.heatmap_size
         heat, _ = ops.gen_targets(d_joints, (self.heatmap_size, self.heatmap_size), (stride, stride),
                                   self.sigma, want_weight=False)

@@ -387,6 +387,30 @@ def frei_joint_2d(kp, center, scale, r):
     return ((j[:, :-1] * 100 + 112) * (FREI_OUT / FREI_RES)).numpy()
 
 
+def color_jitter_sample(chw_f32, fn_idx, b, c, s, h, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    """transforms.ColorJitter.forward with GIVEN parameters followed by transforms.Normalize
+    (src/tools/dataset.py:139-145), through torchvision's own functional ops like the reference (torchvision is
+    its dependency, requirements.yaml:105).  ``fn_idx`` = application order of (0 brightness, 1 contrast,
+    2 saturation, 3 hue); the random draw itself is ``ColorJitter.get_params``."""
+    from torchvision.transforms import functional as F
+    img = torch.from_numpy(np.ascontiguousarray(chw_f32)).float()
+    for fn_id in fn_idx:
+        fn_id = int(fn_id)
+        if fn_id == 0 and b is not None:
+            img = F.adjust_brightness(img, b)
+        elif fn_id == 1 and c is not None:
+            img = F.adjust_contrast(img, c)
+        elif fn_id == 2 and s is not None:
+            img = F.adjust_saturation(img, s)
+        elif fn_id == 3 and h is not None:
+            img = F.adjust_hue(img, h)
+    if mean is not None:
+        m = torch.tensor(mean, dtype=torch.float32).view(-1, 1, 1)
+        sd = torch.tensor(std, dtype=torch.float32).view(-1, 1, 1)
+        img = (img - m) / sd
+    return img.numpy()
+
+
 # ----------------------------------------------------------------------------
 # a-4 / a-5  Gaussian targets
 # ----------------------------------------------------------------------------

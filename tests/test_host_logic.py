@@ -131,3 +131,28 @@ def test_frei_crop_descriptors_follow_the_reference_bookkeeping():
     for pt in ([1, 1], [100.5, 30.25]):
         assert np.array_equal(image_ops.transform(pt, centers[0], scales[0], [224, 224], invert=1, rot=rots[1]),
                               R.frei_transform(pt, centers[0], scales[0], [224, 224], invert=1, rot=rots[1]))
+
+
+def test_color_jitter_draw_follows_torchvision_stream():
+    """tools.dataset.color_jitter_params consumes torch's generator exactly like ColorJitter.get_params
+    (randperm(4), then brightness / contrast / saturation / hue uniforms), sample by sample."""
+    import ctypes
+    from torchvision import transforms
+    from lighthand_b200 import _lib
+    from lighthand_b200.tools.dataset import color_jitter_params
+    assert ctypes.sizeof(_lib.JitterParams) == 52
+    cj = transforms.ColorJitter(brightness=0.5, contrast=0.5, saturation=0.5, hue=0.5)
+    flags = [True, False, True, True]
+    torch.manual_seed(77)
+    want = [cj.get_params(cj.brightness, cj.contrast, cj.saturation, cj.hue) if f else None for f in flags]
+    torch.manual_seed(77)
+    recs = color_jitter_params(flags)
+    for r, w, f in zip(recs, want, flags):
+        assert r.apply == int(f)
+        if not f:
+            assert list(r.order) == [-1] * 4
+            continue
+        fn_idx, b, c, s, h = w
+        assert list(r.order) == [int(v) for v in fn_idx]
+        assert np.allclose(list(r.factor), np.array([b, c, s, h], np.float32), rtol=0, atol=0)
+        assert np.allclose(list(r.one_minus)[:3], np.array([1.0 - b, 1.0 - c, 1.0 - s]).astype(np.float32), rtol=0, atol=0)
