@@ -264,23 +264,35 @@ __global__ void __launch_bounds__(kWThreads) warp_cv2_kernel(const WarpParams p)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Fast uint8 path (LH_INTERP_CV2_U8, 4-byte aligned rows): "pair" staging + IDP.4A.
+// Fast uint8 path (LH_INTERP_CV2_U8, 4-byte aligned rows): record staging + IDP.4A.
 //
-// The source footprint of the 32x32 output tile is staged ONCE into shared memory as 8-byte
-// position records  rec[y][x] = { R[x] R[x+1] G[x] G[x+1] | B[x] B[x+1] - - }  (built with PRMT from
-// 32-bit global loads; positions outside the image hold zeros = cv2's constant border).  A bilinear
-// tap pair is then one LDS.64 per source row, and the horizontal blend of a channel is one IDP.4A
-// against the weight word (32-ax, ax, 0, 0) [<< 16 for G] -- no byte unpacking, no funnel shifts, no
-// per-pixel bounds test.  Lane = output column, so the 32 lanes of a tap load walk neighbouring
+// The source footprint of the 32x32 output tile is staged ONCE into shared memory as position records
+// (built with PRMT from 32-bit global loads; positions outside the image hold zeros = cv2's constant
+// border; the two record formats are described at LH_REC4 below).  A bilinear tap pair of one source
+// row reaches the blend as the words { R[x] R[x+1] G[x] G[x+1] } and { B[x] B[x+1] - - }, so the
+// horizontal blend of a channel is one IDP.4A against the weight word (32-ax, ax, 0, 0) [<< 16 for G]
+// -- no byte unpacking, no funnel shifts, no per-pixel bounds test.  Lane = output column, so the 32 lanes of a tap load walk neighbouring
 // records (bank-conflict free up to the rotation) and every store instruction writes one 128-byte line.
 // The horizontal flip is folded into the coordinate tables exactly:
 //   X' = 32(sw-1) - X  in the 1/32-px fixed-point domain  <=>  X0' = 1024(sw-1) + 31 - X0, adelta' = -adelta.
 // Normalisation: NORM 0 none (0..255), 1 single FMA v*a+b, 2 exact table (torch's three roundings).
 // ------------------------------------------------------------------------------------------------
-#ifndef LH_FAST_MAXPOS
-#define LH_FAST_MAXPOS 3200
+// Record format of the staged window.  LH_REC4 = 1 (default): one 4-byte record {R G B x} per source pixel -- a tap
+// row is two LDS.32 (x, x+1) re-paired by two PRMT into the words the IDP.4A blend wants; half the shared memory of
+// the 8-byte pair records {R[x] R[x+1] G[x] G[x+1] | B[x] B[x+1] - -} (LH_REC4 = 0: one LDS.64 per tap row, no PRMT),
+// so 12 instead of 8 CTAs fit an SM.  Measured on B200 (C2 mix, 256 images): 59.8 us against 68.4 us; the kernel is
+// bound by tiles in flight x tile latency, not by instruction count.
+#ifndef LH_REC4
+#define LH_REC4 1
 #endif
-constexpr int kMaxPos = LH_FAST_MAXPOS;  // position records per CTA (3200 = 25 KB: a 32x32 tile rotated 45 degrees at unit scale is 62 x 49)
+#ifndef LH_FAST_MAXPOS
+#define LH_FAST_MAXPOS (LH_REC4 ? 3328 : 3200)
+#endif
+constexpr int kRecWords = LH_FAST_MAXPOS;   // LH_REC4 = 1: 4-byte records per CTA (3328 = 13 KB: a 32x32 tile rotated 45
+                                            // degrees at unit scale touches 50 x 48 source pixels -> pitch 60 x 49 rows)
+#if !LH_REC4
+constexpr int kMaxPos = LH_FAST_MAXPOS;     // LH_REC4 = 0: 8-byte pair records per CTA (3200 = 25 KB)
+#endif
 
 
 struct TileBox {       // footprint of one output tile in the source, in staged-record coordinates
@@ -325,6 +337,9 @@ __device__ __forceinline__ void warp_rows(const WarpParams& p, const TileBox& bx
                                           int n, int ox, int oy0, int warp) {
     
     const int rec_base = -bx.loy * bx.pitch - bx.cx0;
+#if LH_REC4
+    const uint32_t* s_rec4 = reinterpret_cast<const uint32_t*>(s_rec);
+#endif
     const float na0 = p.mean[0], na1 = p.mean[1], na2 = p.mean[2];   // NORM 1: a, b of v*a + b
     const float nb0 = p.stdv[0], nb1 = p.stdv[1], nb2 = p.stdv[2];
     const int r0 = warp * kRowsPerWarp;
@@ -356,10 +371,19 @@ __device__ __forceinline__ void warp_rows(const WarpParams& p, const TileBox& bx
         uint2 t0, t1;
         if (STAGED) {
             if (CLAMP) { ix = clamp_i(ix, bx.lox, bx.hix); iy = clamp_i(iy, bx.loy, bx.hiy); }
+#if LH_REC4
+            const uint32_t* q = s_rec4 + (iy * bx.pitch + ix + rec_base);
+            LH_BOUNDS(ix >= bx.cx0 && ix + 1 < bx.cx0 + bx.pitch && iy >= bx.loy && iy + 1 < bx.loy + bx.nrows &&
+                      (iy - bx.loy + 1) * bx.pitch + (ix - bx.cx0) + 1 < kRecWords);
+            const uint32_t a0 = q[0], a1 = q[1], b0 = q[bx.pitch], b1 = q[bx.pitch + 1];
+            t0 = make_uint2(__byte_perm(a0, a1, 0x5140), __byte_perm(a0, a1, 0x0062));
+            t1 = make_uint2(__byte_perm(b0, b1, 0x5140), __byte_perm(b0, b1, 0x0062));
+#else
             const uint2* q = s_rec + (iy * bx.pitch + ix + rec_base);
             LH_BOUNDS(ix >= bx.cx0 && ix < bx.cx0 + bx.pitch && iy >= bx.loy && iy + 1 < bx.loy + bx.nrows &&
                       (iy - bx.loy + 1) * bx.pitch + (ix - bx.cx0) < kMaxPos);
             t0 = q[0]; t1 = q[bx.pitch];
+#endif
         } else {
             const uint4 t = taps_from_global(img, p.pitch, p.sw, p.sh, ix, iy);
             t0 = make_uint2(t.x, t.y); t1 = make_uint2(t.z, t.w);
@@ -380,15 +404,20 @@ __device__ __forceinline__ void warp_rows(const WarpParams& p, const TileBox& bx
 }
 
 #ifndef LH_FAST_MINB
-#define LH_FAST_MINB 8
-#endif
+#define LH_FAST_MINB (LH_REC4 ? 12 : 8)    // CTAs per SM the register budget is held to (12 -> 40 registers, no spills;
+#endif                                     // 13+ forces 32 registers and spills: 67 us)
 #ifndef LH_STAGE_DEPTH
 #define LH_STAGE_DEPTH 3
 #endif
 constexpr int kStageDepth = LH_STAGE_DEPTH;   // groups of 4 records whose loads a thread keeps in flight together
 template <int NORM>
 __global__ void __launch_bounds__(kFThreads, LH_FAST_MINB) warp_pairs_kernel(const WarpParams p) {
+#if LH_REC4
+    __shared__ __align__(16) uint32_t s_rec_w[kRecWords];
+    uint2* const s_rec = reinterpret_cast<uint2*>(s_rec_w);
+#else
     __shared__ __align__(16) uint2 s_rec[kMaxPos];
+#endif
     __shared__ float s_lut[NORM == 2 ? 768 : 1];
     __shared__ int s_ad[kTileW], s_bd[kTileW];
     __shared__ __align__(16) int s_x0[kTileH], s_y0[kTileH];
@@ -437,6 +466,14 @@ __global__ void __launch_bounds__(kFThreads, LH_FAST_MINB) warp_pairs_kernel(con
             bx.loy = clamp_i(iymin, -2, p.sh); bx.hiy = clamp_i(iymax, -2, p.sh);
             const bool need_clamp = (bx.lox != ixmin) | (bx.hix != ixmax) | (bx.loy != iymin) | (bx.hiy != iymax);
             bx.cx0 = bx.lox & ~3;                               // staged columns start at a multiple of 4 records
+#if LH_REC4
+            // one record per source pixel: columns lox .. hix + 1 (the right tap); a row is a multiple of 4 records
+            // (16-byte aligned for the STS.128 of the staging pass) and an odd multiple of 4 (bank skew between rows)
+            bx.gpr = ((bx.hix + 1 - bx.cx0 + 1) + 3) >> 2;
+            bx.pitch = ((4 * bx.gpr + 7) & ~7) + 4;
+            bx.nrows = bx.hiy - bx.loy + 2;                     // rows loy .. hiy+1
+            const bool staged = (bx.pitch <= 256) && (bx.nrows * bx.pitch <= kRecWords);
+#else
             // records per staged row: a multiple of 8 plus 6 (rows stay 16-byte aligned for the STS.128 of the
             // staging pass).  Measured with ncu on the benchmark's rotation mix: the +6 skew between rows cuts the
             // bank conflicts of the LDS.64 tap loads by ~30 % and those of the staging stores by ~20 % against a
@@ -446,8 +483,9 @@ __global__ void __launch_bounds__(kFThreads, LH_FAST_MINB) warp_pairs_kernel(con
             // pitch <= 256 keeps the reciprocal-multiply row split below exact (g * gpr < 2^20)
             const bool staged = (bx.pitch <= 256) && (bx.nrows * bx.pitch <= kMaxPos);
             bx.gpr = ((bx.hix - bx.cx0 + 1) + 3) >> 2;          // only the columns that can be touched are staged
+#endif
             const bool interior = (bx.loy >= 0) & (bx.loy + bx.nrows <= p.sh) & (bx.cx0 >= 0) &
-                                  (bx.cx0 + 4 * bx.gpr + 1 <= p.sw);
+                                  (bx.cx0 + 4 * bx.gpr + (LH_REC4 ? 0 : 1) <= p.sw);
             bx.flags = (staged ? 1 : 0) | (need_clamp ? 2 : 0) | (interior ? 4 : 0);
             bx.total = bx.nrows * bx.gpr;
             bx.inv = ((1u << 20) + bx.gpr - 1) / bx.gpr;
@@ -472,6 +510,51 @@ __global__ void __launch_bounds__(kFThreads, LH_FAST_MINB) warp_pairs_kernel(con
         const bool interior = bx.flags & 4;
         const uint8_t* org = img + (long long)bx.loy * p.pitch + 3 * bx.cx0;
         const int rowb = 3 * p.sw;
+#if LH_REC4
+        // a group = 4 source pixels = 3 words -> 4 records {R G B x} (byte 3 is don't-care: it only ever meets a zero
+        // weight); one STS.128 per group
+        uint32_t* const s_w = reinterpret_cast<uint32_t*>(s_rec);
+        for (int g0 = tid; g0 < bx.total; g0 += kStageDepth * kFThreads) {
+            uint32_t w[kStageDepth][3];
+#pragma unroll
+            for (int i = 0; i < kStageDepth; ++i) {
+                const int g = g0 + i * kFThreads;
+                w[i][0] = w[i][1] = w[i][2] = 0u;
+                if (g < bx.total) {
+                    const int r = (int)((g * bx.inv) >> 20), k = g - r * bx.gpr;
+                    if (interior) {
+                        const uint32_t* rp = reinterpret_cast<const uint32_t*>(org + (long long)r * p.pitch) + 3 * k;
+                        w[i][0] = __ldg(rp); w[i][1] = __ldg(rp + 1); w[i][2] = __ldg(rp + 2);
+                    } else {
+                        const int y = bx.loy + r, bo = 3 * (bx.cx0 + 4 * k);
+                        if (y >= 0 && y < p.sh) {
+                            const uint32_t* rp = reinterpret_cast<const uint32_t*>(img + (long long)y * p.pitch);
+                            if (bo >= 0 && bo < rowb) w[i][0] = __ldg(rp + (bo >> 2));
+                            if (bo + 4 >= 0 && bo + 4 < rowb) w[i][1] = __ldg(rp + (bo >> 2) + 1);
+                            if (bo + 8 >= 0 && bo + 8 < rowb) w[i][2] = __ldg(rp + (bo >> 2) + 2);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kStageDepth; ++i) {
+                const int g = g0 + i * kFThreads;
+                if (g >= bx.total) continue;
+                const int r = (int)((g * bx.inv) >> 20), k = g - r * bx.gpr;
+                const uint32_t w0 = w[i][0], w1 = w[i][1], w2 = w[i][2];
+                uint32_t px[4] = {w0, __byte_perm(w0, w1, 0x0543), __byte_perm(w1, w2, 0x0432), w2 >> 8};
+                if (!interior) {
+                    const int y = bx.loy + r, x = bx.cx0 + 4 * k;
+                    const bool yin = (y >= 0) & (y < p.sh);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)     // pixels outside the image are the constant border 0
+                        if (!(yin && (x + q >= 0) && (x + q < p.sw))) px[q] = 0u;
+                }
+                LH_BOUNDS(r >= 0 && r < bx.nrows && k >= 0 && 4 * k + 3 < bx.pitch && r * bx.pitch + 4 * k + 3 < kRecWords);
+                *reinterpret_cast<uint4*>(s_w + r * bx.pitch + 4 * k) = make_uint4(px[0], px[1], px[2], px[3]);
+            }
+        }
+#else
         for (int g0 = tid; g0 < bx.total; g0 += kStageDepth * kFThreads) {
             uint32_t w[kStageDepth][4];
 #pragma unroll
@@ -523,6 +606,7 @@ __global__ void __launch_bounds__(kFThreads, LH_FAST_MINB) warp_pairs_kernel(con
                 d[1] = make_uint4(a[2], c[2], a[3], c[3]);
             }
         }
+#endif
     }
     __syncthreads();
     LH_TICK(t_stage);
