@@ -671,19 +671,20 @@ __global__ void __launch_bounds__(kWThreads) resize_torch_kernel(const WarpParam
 
 // ------------------------------------------------------------------------------------------------
 // Fast resize path (LH_INTERP_TORCH without flip / gain, 4-byte aligned rows): same structure as
-// warp_pairs_kernel -- the source window of a 32x32 output tile is staged once as pair records
-// {R[x] R[x+1] G[x] G[x+1] | B[x] B[x+1]} (right edge clamped, like torch's min(x0+1, in-1)), lane = output
-// column, a warp renders 8 rows; per pixel two LDS.64, byte->float conversions and 7 float ops per channel.
+// warp_pairs_kernel -- the source window of a 32x32 output tile is staged once as 4-byte records {R G B x}
+// (one column past the right edge repeats the last pixel, like torch's min(x0+1, in-1)), lane = output
+// column, a warp renders 8 rows; per pixel four LDS.32, byte->float conversions and 7 float ops per channel.
+// 12 CTAs per SM (11 KB of records each): like the warp kernel this one is bound by tiles in flight.
 // The interpolation weights are torch's (area_pixel_compute_source_index, align_corners=False); the value is
 // computed in byte units and scaled once, v*a + b with a = 1/(255 std), b = -mean/std: within ~3 ulp of the
 // exact-order kernel below (which stays the path for flip / gain / unaligned rows) and far inside the 1e-5
 // tolerance of this mode.
 // ------------------------------------------------------------------------------------------------
-constexpr int kRMaxPos = 2304;   // 18 KB: up to 48 x 48 source records per 32x32 output tile (scale <= 1.4)
+constexpr int kRMaxPos = 2880;   // 11.25 KB of 4-byte records: up to 60 x 48 per 32x32 output tile (scale <= 1.4)
 
-__global__ void __launch_bounds__(kFThreads, 8) resize_pairs_kernel(const WarpParams p) {
+__global__ void __launch_bounds__(kFThreads, 12) resize_pairs_kernel(const WarpParams p) {
     static_assert(kFThreads == 128 && kTileH == 32 && kRowsPerWarp == 8, "tile roles below assume 4 warps x 8 rows");
-    __shared__ __align__(16) uint2 s_rec[kRMaxPos];
+    __shared__ __align__(16) uint32_t s_rec[kRMaxPos];
     __shared__ int s_cx[kTileW];                       // record column of each output column (window-relative)
     __shared__ float s_lx[kTileW];                     // lambda_1 of each output column
     __shared__ __align__(16) int s_r0[kTileH], s_r1[kTileH];   // record rows (window-relative) of each output row
@@ -706,7 +707,8 @@ __global__ void __launch_bounds__(kFThreads, 8) resize_pairs_kernel(const WarpPa
     const int x_hi = min((int)src_index(sx, tx0 + cl), p.sw - 1);
     const int y_lo = min((int)src_index(sy, ty0), p.sh - 1);
     const int y_hi = min(min((int)src_index(sy, ty0 + rl), p.sh - 1) + 1, p.sh - 1);
-    const int gpr = (x_hi - x_lo + 4) >> 2, pitch = ((4 * gpr + 7) & ~7) + 6, nrows = y_hi - y_lo + 1;
+    // columns x_lo .. x_hi + 1 (the right tap); rows are a multiple of 4 records, an odd one (bank skew between rows)
+    const int gpr = (x_hi - x_lo + 5) >> 2, pitch = ((4 * gpr + 7) & ~7) + 4, nrows = y_hi - y_lo + 1;
     if (warp == 0) {
         const float f = src_index(sx, tx0 + min(lane, cl));
         const int x0 = min((int)f, p.sw - 1);
@@ -719,35 +721,27 @@ __global__ void __launch_bounds__(kFThreads, 8) resize_pairs_kernel(const WarpPa
         s_r1[lane] = min(y0 + 1, p.sh - 1) - y_lo;
         s_ly[lane] = fminf(fmaxf(__fsub_rn(f, (float)y0), 0.f), 1.f);
     }
-    // stage the window (every staged row lies inside the image; only the last column needs the clamp)
+    // stage the window (every staged row lies inside the image; columns at or beyond the right edge repeat the
+    // last pixel): a group = 4 pixels = 3 words -> 4 records, one STS.128
     const int total = nrows * gpr;
     const unsigned inv = ((1u << 20) + gpr - 1) / gpr;
-    const int rowb = 3 * p.sw;
     for (int g = tid; g < total; g += kFThreads) {
         const int r = (int)((g * inv) >> 20), k = g - r * gpr;
-        const int x = x_lo + 4 * k, bo = 3 * x;
-        const uint32_t* rp = reinterpret_cast<const uint32_t*>(img + (long long)(y_lo + r) * p.pitch) + (bo >> 2);
-        uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-        if (bo < rowb) w0 = __ldg(rp);
-        if (bo + 4 < rowb) w1 = __ldg(rp + 1);
-        if (bo + 8 < rowb) w2 = __ldg(rp + 2);
-        if (bo + 12 < rowb) w3 = __ldg(rp + 3);
-        uint32_t a[4] = {__byte_perm(w0, w1, 0x4130), __byte_perm(w0, w1, 0x7463),
-                         __byte_perm(w1, w2, 0x6352), __byte_perm(w2, w3, 0x5241)};
-        uint32_t c[4] = {__byte_perm(w0, w1, 0x0052), __byte_perm(w1, w2, 0x0041),
-                         __byte_perm(w2, w2, 0x0030), __byte_perm(w2, w3, 0x0063)};
-        if (x + 4 >= p.sw) {
+        const int x = x_lo + 4 * k;
+        const uint8_t* row = img + (long long)(y_lo + r) * p.pitch;
+        uint32_t px[4];
+        if (x + 3 < p.sw) {
+            const uint32_t* rp = reinterpret_cast<const uint32_t*>(row) + 3 * (x >> 2);
+            const uint32_t w0 = __ldg(rp), w1 = __ldg(rp + 1), w2 = __ldg(rp + 2);
+            px[0] = w0; px[1] = __byte_perm(w0, w1, 0x0543); px[2] = __byte_perm(w1, w2, 0x0432); px[3] = w2 >> 8;
+        } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                if (x + i + 1 >= p.sw) {     // x1 = min(x0 + 1, in - 1): the pair's second pixel is the first one
-                    a[i] = __byte_perm(a[i], 0, 0x2200);
-                    c[i] = __byte_perm(c[i], 0, 0x4400);
-                }
+                const uint8_t* q = row + 3 * min(x + i, p.sw - 1);
+                px[i] = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16);
             }
         }
-        uint4* d = reinterpret_cast<uint4*>(s_rec + r * pitch + 4 * k);
-        d[0] = make_uint4(a[0], c[0], a[1], c[1]);
-        d[1] = make_uint4(a[2], c[2], a[3], c[3]);
+        *reinterpret_cast<uint4*>(s_rec + r * pitch + 4 * k) = make_uint4(px[0], px[1], px[2], px[3]);
     }
     __syncthreads();
 
@@ -776,14 +770,16 @@ __global__ void __launch_bounds__(kFThreads, 8) resize_pairs_kernel(const WarpPa
         if (j >= rows) break;
         const int r = r0w + j;
         const float ly1 = s_ly[r], ly0 = __fsub_rn(1.0f, ly1);
-        const uint2 t0 = s_rec[s_r0[r] * pitch + cx], t1 = s_rec[s_r1[r] * pitch + cx];
-        auto lerp2 = [&](uint32_t w0_, uint32_t w1_, int sh_) {
-            const float p00 = (float)((w0_ >> sh_) & 0xffu), p01 = (float)((w0_ >> (sh_ + 8)) & 0xffu);
-            const float p10 = (float)((w1_ >> sh_) & 0xffu), p11 = (float)((w1_ >> (sh_ + 8)) & 0xffu);
+        const uint32_t* q0 = s_rec + s_r0[r] * pitch + cx;
+        const uint32_t* q1 = s_rec + s_r1[r] * pitch + cx;
+        const uint32_t a0 = q0[0], a1 = q0[1], b0 = q1[0], b1 = q1[1];
+        auto lerp2 = [&](int sh_) {
+            const float p00 = (float)((a0 >> sh_) & 0xffu), p01 = (float)((a1 >> sh_) & 0xffu);
+            const float p10 = (float)((b0 >> sh_) & 0xffu), p11 = (float)((b1 >> sh_) & 0xffu);
             const float top = fmaf(lx1, p01, lx0 * p00), bot = fmaf(lx1, p11, lx0 * p10);
             return fmaf(ly1, bot, ly0 * top);
         };
-        const float vr = lerp2(t0.x, t1.x, 0), vg = lerp2(t0.x, t1.x, 16), vb = lerp2(t0.y, t1.y, 0);
+        const float vr = lerp2(0), vg = lerp2(8), vb = lerp2(16);
         __stcs(p.dst + i0, fmaf(vr, na0, nb0));
         __stcs(p.dst + i1, fmaf(vg, na1, nb1));
         __stcs(p.dst + i2, fmaf(vb, na2, nb2));
@@ -883,7 +879,7 @@ extern "C" int lh_warp_normalize(const uint8_t* src, int64_t src_img_stride, int
         // source records needed by one 32x32 output tile: (32 * in/out + 2 + alignment)^2 must fit the staging buffer
         const double fx = 32.0 * src_w / out_w + 8.0, fy = 32.0 * src_h / out_h + 3.0;
         const long long per_img = 3LL * out_h * out_w;
-        const bool fits = (((int)fx + 7) / 8 * 8 + 6) * (long long)((int)fy + 1) <= kRMaxPos;
+        const bool fits = (((int)fx + 7) / 8 * 8 + 4) * (long long)((int)fy + 1) <= kRMaxPos;
         if (words && fits && !flip && !chan_gain && per_img * N < (1LL << 31)) {
             WarpParams q = p;
             for (int i = 0; i < 3; ++i) {        // v (byte units) * a + b
