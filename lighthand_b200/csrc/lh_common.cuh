@@ -64,7 +64,7 @@ __device__ __forceinline__ int sat_i32(double v) {
 __device__ __forceinline__ void invert_affine(const double* M, double* o) {
     double m0 = M[0], m1 = M[1], m2 = M[2], m3 = M[3], m4 = M[4], m5 = M[5];
     double D = __dsub_rn(__dmul_rn(m0, m4), __dmul_rn(m1, m3));
-    D = (D != 0.0) ? __ddiv_rn(1.0, D) : 0.0;
+    D = (D != 0.0) ? __drcp_rn(D) : 0.0;      // correctly rounded 1 / D, like the division OpenCV performs
     const double a11 = __dmul_rn(m4, D), a22 = __dmul_rn(m0, D);
     m0 = a11; m1 = __dmul_rn(m1, -D); m3 = __dmul_rn(m3, -D); m4 = a22;
     const double b1 = __dsub_rn(__dmul_rn(-m0, m2), __dmul_rn(m1, m5));
