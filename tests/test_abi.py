@@ -74,3 +74,10 @@ def test_header_is_plain_c_and_the_c_host_links(tmp_path):
     subprocess.run(["gcc", "-std=c11", "-O1", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
                     os.path.join(ROOT, "tests", "c", "abi_host_demo.c"), "-o", str(tmp_path / "demo"), "-L", libdir,
                     "-llighthand_b200", "-lm"], check=True)
+
+
+def test_graft_build_entry_point():
+    """__graft_entry__.build() is what the driver runs as the does-it-build check: it must agree with the header's
+    ABI version (an up-to-date tree makes this a no-op `make`)."""
+    import __graft_entry__ as g
+    g.build()
