@@ -219,11 +219,11 @@ typedef struct lh_frei_desc {
 
 /* rgb_processing for N images: out dev [N,3,res,res] float32 in 0..1 (CHW, /255, noise applied).
  * desc dev [N]; rot_index dev int32 [n_rot] = indices of the samples with rotated != 0 (NULL: every sample is
- * visited and the flag decides); scratch dev float (sum of the rotated canvases) or NULL when max_rot_px == 0;
- * max_rot_px = max over rotated samples of (cw-2pad)*(ch-2pad) (0: no sample is rotated). */
+ * visited and the flag decides); scratch dev float (sum of the rotated canvases) or NULL when no sample is rotated;
+ * max_rot_w / max_rot_h = max over rotated samples of cw-2pad / ch-2pad (both 0: no sample is rotated). */
 int lh_frei_rgb_processing(const uint8_t* src, int64_t src_img_stride, int src_h, int src_w, int src_pitch,
                            const lh_frei_desc* desc, int N, int res, const int32_t* rot_index, int n_rot,
-                           float* scratch, int64_t max_rot_px, float* out, lh_stream_t stream);
+                           float* scratch, int max_rot_w, int max_rot_h, float* out, lh_stream_t stream);
 
 /* transforms.Resize((out_h,out_w)) on a float CHW batch (bilinear, align_corners=False, no antialias; ATen's
  * float32 operation order, within ~1 ulp of torch) + Normalize as one multiply-add (mean_std host [6] or NULL;

@@ -31,35 +31,62 @@ __device__ __forceinline__ void canvas_px(const uint8_t* img, int pitch, int sh,
     v[0] = (float)__ldg(q); v[1] = (float)__ldg(q + 1); v[2] = (float)__ldg(q + 2);
 }
 
+// three channels of canvas pixel (cx, cy) known to lie inside both the canvas and the image
+__device__ __forceinline__ void image_px(const uint8_t* org, int pitch, int cx, int cy, float (&v)[3]) {
+    const uint8_t* q = org + (long long)cy * pitch + 3 * cx;
+    v[0] = (float)__ldg(q); v[1] = (float)__ldg(q + 1); v[2] = (float)__ldg(q + 2);
+}
+
+constexpr int kFreiTileW = 32, kFreiTileH = kFreiThreads / 32;
+
+// CTA = a 32 x 8 tile of the rotated canvas of one rotated sample (blockIdx.z indexes rot_index): the FP64 row and
+// column terms of cv2's coordinate grid are computed once per tile (40 threads), not once per pixel
 __global__ void __launch_bounds__(kFreiThreads) frei_rotate_kernel(const uint8_t* __restrict__ src, long long img_stride,
                                                                    int sh, int sw, int pitch,
                                                                    const lh_frei_desc* __restrict__ desc,
                                                                    const int32_t* __restrict__ rot_index,
                                                                    float* __restrict__ scratch) {
-    const int n = rot_index ? rot_index[blockIdx.y] : blockIdx.y;
-    const lh_frei_desc d = desc[n];
+    __shared__ int s_ax[kFreiTileW], s_bx[kFreiTileW], s_x0[kFreiTileH], s_y0[kFreiTileH];
+    const int n = rot_index ? rot_index[blockIdx.z] : blockIdx.z;
+    const lh_frei_desc& d = desc[n];
     if (!d.rotated) return;
-    const double* s_im = d.iM;
-    const int iw = d.cw - 2 * d.pad, ih = d.ch - 2 * d.pad;
+    const int pad = d.pad, iw = d.cw - 2 * pad, ih = d.ch - 2 * pad;
+    const int tx0 = blockIdx.x * kFreiTileW, ty0 = blockIdx.y * kFreiTileH;
+    if (tx0 >= iw || ty0 >= ih) return;                                  // uniform per CTA
+    const int tid = threadIdx.x;
+    if (tid < kFreiTileW) {
+        s_ax[tid] = col_term(d.iM[0], tx0 + tid + pad);                  // position in the padded canvas warpAffine renders
+        s_bx[tid] = col_term(d.iM[3], tx0 + tid + pad);
+    } else if (tid < kFreiTileW + kFreiTileH) {
+        const int r = tid - kFreiTileW;
+        s_x0[r] = row_term(d.iM[1], d.iM[2], ty0 + r + pad);
+        s_y0[r] = row_term(d.iM[4], d.iM[5], ty0 + r + pad);
+    }
+    __syncthreads();
+    const int lx = tid & 31, ly = tid >> 5;
+    const int x = tx0 + lx, y = ty0 + ly;
+    if (x >= iw || y >= ih) return;
+    const int X = (s_x0[ly] + s_ax[lx]) >> 5, Y = (s_y0[ly] + s_bx[lx]) >> 5;
+    const int ix = clamp_i(X >> 5, -32768, 32767), iy = clamp_i(Y >> 5, -32768, 32767);   // cv2 stores shorts
+    const float fx = (float)(X & 31) * 0.03125f, fy = (float)(Y & 31) * 0.03125f;
+    const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
     const uint8_t* img = src + (long long)n * img_stride;
-    float* out = scratch + d.scratch_off;
-    for (int idx = blockIdx.x * kFreiThreads + threadIdx.x; idx < iw * ih; idx += gridDim.x * kFreiThreads) {
-        const int y = idx / iw, x = idx - y * iw;
-        const int dx = x + d.pad, dy = y + d.pad;          // position in the padded canvas warpAffine renders
-        const int X = (row_term(s_im[1], s_im[2], dy) + col_term(s_im[0], dx)) >> 5;
-        const int Y = (row_term(s_im[4], s_im[5], dy) + col_term(s_im[3], dx)) >> 5;
-        const int ix = clamp_i(X >> 5, -32768, 32767), iy = clamp_i(Y >> 5, -32768, 32767);   // cv2 stores shorts
-        const float fx = (float)(X & 31) * 0.03125f, fy = (float)(Y & 31) * 0.03125f;
-        const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
-        float p00[3], p01[3], p10[3], p11[3];
+    float p00[3], p01[3], p10[3], p11[3];
+    // all four taps inside the canvas and inside the image: no per-tap tests
+    const int gx = d.ulx + ix, gy = d.uly + iy;
+    if (ix >= 0 && iy >= 0 && ix + 1 < d.cw && iy + 1 < d.ch && gx >= 0 && gy >= 0 && gx + 1 < sw && gy + 1 < sh) {
+        image_px(img, pitch, gx, gy, p00); image_px(img, pitch, gx + 1, gy, p01);
+        image_px(img, pitch, gx, gy + 1, p10); image_px(img, pitch, gx + 1, gy + 1, p11);
+    } else {
         canvas_px(img, pitch, sh, sw, d, ix, iy, p00);
         canvas_px(img, pitch, sh, sw, d, ix + 1, iy, p01);
         canvas_px(img, pitch, sh, sw, d, ix, iy + 1, p10);
         canvas_px(img, pitch, sh, sw, d, ix + 1, iy + 1, p11);
-#pragma unroll
-        for (int c = 0; c < 3; ++c)    // every product and partial sum is exact in float32 (<= 18 bits)
-            out[(size_t)idx * 3 + c] = p00[c] * w00 + p01[c] * w01 + p10[c] * w10 + p11[c] * w11;
     }
+    float* out = scratch + d.scratch_off + ((size_t)y * iw + x) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)    // every product and partial sum is exact in float32 (<= 18 bits)
+        out[c] = p00[c] * w00 + p01[c] * w01 + p10[c] * w10 + p11[c] * w11;
 }
 
 // cv2.resize's source index / weight for destination index d (resize.cpp, INTER_LINEAR, CV_64F): double
@@ -74,26 +101,38 @@ __device__ __forceinline__ void cv2_linear_axis(int d, int ssize, double scale, 
     w0 = (float)__dsub_rn(1.0, f); w1 = (float)f;
 }
 
+// CTA = a 32 x 8 tile of the res x res output of one sample; cv2.resize's double-precision source indices and
+// weights are computed once per tile column / row (40 threads)
 __global__ void __launch_bounds__(kFreiThreads) frei_resize_kernel(const uint8_t* __restrict__ src, long long img_stride,
                                                                    int sh, int sw, int pitch,
                                                                    const lh_frei_desc* __restrict__ desc,
                                                                    const float* __restrict__ scratch, int res,
                                                                    float* __restrict__ dst) {
+    __shared__ int s_x0[kFreiTileW], s_x1[kFreiTileW], s_y0[kFreiTileH], s_y1[kFreiTileH];
+    __shared__ float s_a0[kFreiTileW], s_a1[kFreiTileW], s_b0[kFreiTileH], s_b1[kFreiTileH];
     const int n = blockIdx.z;
-    const lh_frei_desc d = desc[n];
-    const int pad = d.rotated ? d.pad : 0;
+    const lh_frei_desc& d = desc[n];
+    const int rotated = d.rotated;
+    const int pad = rotated ? d.pad : 0;
     const int iw = d.cw - 2 * pad, ih = d.ch - 2 * pad;
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * (kFreiThreads / 32) + (threadIdx.x >> 5);
+    const int tid = threadIdx.x;
+    const int tx0 = blockIdx.x * kFreiTileW, ty0 = blockIdx.y * kFreiTileH;
+    if (iw > 0 && ih > 0) {
+        if (tid < kFreiTileW) cv2_linear_axis(tx0 + tid, iw, d.scale_x, s_x0[tid], s_x1[tid], s_a0[tid], s_a1[tid]);
+        else if (tid < kFreiTileW + kFreiTileH)
+            cv2_linear_axis(ty0 + tid - kFreiTileW, ih, d.scale_y, s_y0[tid - kFreiTileW], s_y1[tid - kFreiTileW],
+                            s_b0[tid - kFreiTileW], s_b1[tid - kFreiTileW]);
+    }
+    __syncthreads();
+    const int lx = tid & 31, ly = tid >> 5;
+    const int x = tx0 + lx, y = ty0 + ly;
     if (x >= res || y >= res) return;
     float* o = dst + (size_t)n * 3 * res * res + (size_t)y * res + x;
     if (iw <= 0 || ih <= 0) { o[0] = 0.f; o[(size_t)res * res] = 0.f; o[2 * (size_t)res * res] = 0.f; return; }
-    const double scx = d.scale_x, scy = d.scale_y;     // 1 / (res / iw), 1 / (res / ih): host, double, like OpenCV
-    int x0, x1, y0, y1;
-    float a0, a1, b0, b1;
-    cv2_linear_axis(x, iw, scx, x0, x1, a0, a1);
-    cv2_linear_axis(y, ih, scy, y0, y1, b0, b1);
+    const int x0 = s_x0[lx], x1 = s_x1[lx], y0 = s_y0[ly], y1 = s_y1[ly];
+    const float a0 = s_a0[lx], a1 = s_a1[lx], b0 = s_b0[ly], b1 = s_b1[ly];
     float p00[3], p01[3], p10[3], p11[3];
-    if (d.rotated) {
+    if (rotated) {
         const float* r0 = scratch + d.scratch_off + (size_t)y0 * iw * 3;
         const float* r1 = scratch + d.scratch_off + (size_t)y1 * iw * 3;
 #pragma unroll
@@ -103,16 +142,23 @@ __global__ void __launch_bounds__(kFreiThreads) frei_resize_kernel(const uint8_t
         }
     } else {
         const uint8_t* img = src + (long long)n * img_stride;
-        canvas_px(img, pitch, sh, sw, d, x0, y0, p00);
-        canvas_px(img, pitch, sh, sw, d, x1, y0, p01);
-        canvas_px(img, pitch, sh, sw, d, x0, y1, p10);
-        canvas_px(img, pitch, sh, sw, d, x1, y1, p11);
+        const int gx0 = d.ulx + x0, gx1 = d.ulx + x1, gy0 = d.uly + y0, gy1 = d.uly + y1;   // x0 <= x1 < cw, y0 <= y1 < ch
+        if (gx0 >= 0 && gy0 >= 0 && gx1 < sw && gy1 < sh) {
+            image_px(img, pitch, gx0, gy0, p00); image_px(img, pitch, gx1, gy0, p01);
+            image_px(img, pitch, gx0, gy1, p10); image_px(img, pitch, gx1, gy1, p11);
+        } else {
+            canvas_px(img, pitch, sh, sw, d, x0, y0, p00);
+            canvas_px(img, pitch, sh, sw, d, x1, y0, p01);
+            canvas_px(img, pitch, sh, sw, d, x0, y1, p10);
+            canvas_px(img, pitch, sh, sw, d, x1, y1, p11);
+        }
     }
+    const float pn[3] = {d.pn[0], d.pn[1], d.pn[2]};
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const float top = fmaf(p01[c], a1, p00[c] * a0), bot = fmaf(p11[c], a1, p10[c] * a0);   // rows first ...
         float v = fmaf(bot, b1, top * b0);                                                       // ... then columns
-        v = fminf(255.0f, fmaxf(0.0f, v * d.pn[c]));          // pixel noise + clip (frei_dataloader.py:142-144)
+        v = fminf(255.0f, fmaxf(0.0f, v * pn[c]));            // pixel noise + clip (frei_dataloader.py:142-144)
         o[(size_t)c * res * res] = v * (1.0f / 255.0f);       // CHW float32 / 255 (:146), <= 1 ulp from the division
     }
 }
@@ -170,19 +216,21 @@ __global__ void __launch_bounds__(kFreiThreads) resize_f32_kernel(const float* _
 
 extern "C" int lh_frei_rgb_processing(const uint8_t* src, int64_t src_img_stride, int src_h, int src_w, int src_pitch,
                                       const lh_frei_desc* desc, int N, int res, const int32_t* rot_index, int n_rot,
-                                      float* scratch, int64_t max_rot_px, float* out, lh_stream_t stream) {
-    if (N < 0 || res <= 0 || src_h <= 0 || src_w <= 0 || src_pitch < 3 * src_w || max_rot_px < 0 || n_rot < 0 || n_rot > N)
+                                      float* scratch, int max_rot_w, int max_rot_h, float* out, lh_stream_t stream) {
+    if (N < 0 || res <= 0 || src_h <= 0 || src_w <= 0 || src_pitch < 3 * src_w || max_rot_w < 0 || max_rot_h < 0 ||
+        (max_rot_w > 0) != (max_rot_h > 0) || n_rot < 0 || n_rot > N)
         return LH_EINVAL;
     if (N == 0) return LH_OK;
-    if (!src || !desc || !out || (max_rot_px > 0 && !scratch)) return LH_ENULL;
-    if (N > 65535 || res > 32768 || max_rot_px > (int64_t)1 << 30) return LH_EINVAL;
+    if (!src || !desc || !out || (max_rot_w > 0 && !scratch)) return LH_ENULL;
+    if (N > 65535 || res > 32768 || max_rot_w > 32768 || max_rot_h > 32768) return LH_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    if (max_rot_px > 0) {
-        const int gx = (int)((max_rot_px + lh::kFreiThreads - 1) / lh::kFreiThreads);
-        const int ny = rot_index ? n_rot : N;      // with the list only the rotated samples get CTAs
-        if (ny > 0)
-            lh::frei_rotate_kernel<<<dim3(gx, ny), lh::kFreiThreads, 0, st>>>(src, (long long)src_img_stride, src_h, src_w,
-                                                                            src_pitch, desc, rot_index, scratch);
+    if (max_rot_w > 0) {
+        const int mw = max_rot_w, mh = max_rot_h;
+        const int nz = rot_index ? n_rot : N;      // with the list only the rotated samples get CTAs
+        if (nz > 0)
+            lh::frei_rotate_kernel<<<dim3((mw + lh::kFreiTileW - 1) / lh::kFreiTileW, (mh + lh::kFreiTileH - 1) / lh::kFreiTileH, nz),
+                                     lh::kFreiThreads, 0, st>>>(src, (long long)src_img_stride, src_h, src_w, src_pitch, desc,
+                                                                rot_index, scratch);
         LH_CHECK_LAUNCH();
     }
     const int rows = lh::kFreiThreads / 32;

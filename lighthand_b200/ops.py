@@ -164,7 +164,7 @@ def warp_normalize(images_u8: torch.Tensor, fwd_affine: Optional[torch.Tensor], 
 # ---------------------------------------------------------------------------------------------
 
 def frei_rgb_processing(images_u8: torch.Tensor, desc: torch.Tensor, res: int, scratch_floats: int,
-                        max_rot_px: int, out: Optional[torch.Tensor] = None,
+                        max_rot_wh: Sequence[int], out: Optional[torch.Tensor] = None,
                         rot_index: Optional[torch.Tensor] = None) -> torch.Tensor:
     """rgb_processing (src/datasets/frei_dataloader.py:134-147) of a batch.  images_u8 [N,H,W,3] uint8 CUDA;
     ``desc`` = uint8 CUDA tensor holding N packed ``lh_frei_desc`` records (utils.image_ops.crop_descriptors);
@@ -186,13 +186,14 @@ def frei_rgb_processing(images_u8: torch.Tensor, desc: torch.Tensor, res: int, s
             raise LighthandError("out: wrong shape")
     if n == 0:
         return out
-    scratch = torch.empty(int(scratch_floats), dtype=torch.float32, device=images_u8.device) if max_rot_px > 0 else None
+    max_w, max_h = int(max_rot_wh[0]), int(max_rot_wh[1])
+    scratch = torch.empty(int(scratch_floats), dtype=torch.float32, device=images_u8.device) if max_w > 0 else None
     if rot_index is not None:
         rot_index = _dev(rot_index, torch.int32, "rot_index")
     with torch.cuda.device(images_u8.device):
         check(lib.lh_frei_rgb_processing(images_u8.data_ptr(), sh * sw * 3, sh, sw, sw * 3, desc.data_ptr(), n, int(res),
                                          _ptr(rot_index), 0 if rot_index is None else rot_index.numel(),
-                                         _ptr(scratch), int(max_rot_px), out.data_ptr(), _stream()),
+                                         _ptr(scratch), max_w, max_h, out.data_ptr(), _stream()),
               "lh_frei_rgb_processing")
     return out
 

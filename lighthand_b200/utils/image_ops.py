@@ -80,10 +80,10 @@ def invert_affine_cv2(m):
 
 def crop_descriptors(centers, scales, res, rots, pns=None):
     """Host half of ``crop`` for a batch (src/utils/image_ops.py:99-106): returns (records, scratch_floats,
-    max_rot_px) where ``records`` is a ctypes array of ``lh_frei_desc``."""
+    (max_rot_w, max_rot_h)) where ``records`` is a ctypes array of ``lh_frei_desc``."""
     n = len(scales)
     recs = (_lib.FreiDesc * n)()
-    off, max_px = 0, 0
+    off, max_w, max_h = 0, 0, 0
     for i in range(n):
         center, scale, rot = centers[i], float(scales[i]), float(rots[i])
         ul = np.array(transform([1, 1], center, scale, res, invert=1)) - 1
@@ -110,12 +110,12 @@ def crop_descriptors(centers, scales, res, rots, pns=None):
                 raise LighthandError("crop: nothing left after removing the rotation padding")
             r.scratch_off = off
             off += 3 * iw * ih
-            max_px = max(max_px, iw * ih)
+            max_w, max_h = max(max_w, iw), max(max_h, ih)
         r.scale_x = 1.0 / (float(res[0]) / float(iw))      # cv2.resize: scale = 1 / inv_scale, inv_scale = dsize / ssize
         r.scale_y = 1.0 / (float(res[1]) / float(ih))
         pn = (1.0, 1.0, 1.0) if pns is None else pns[i]
         r.pn[0], r.pn[1], r.pn[2] = float(pn[0]), float(pn[1]), float(pn[2])
-    return recs, off, max_px
+    return recs, off, (max_w, max_h)
 
 
 def descriptors_to_device(recs, device) -> torch.Tensor:
@@ -128,10 +128,10 @@ def crop_batch(images_u8: torch.Tensor, centers, scales, res, rots, pns=None) ->
     [N,H,W,3] -> float32 [N,3,res,res] in 0..1 (rgb_processing's result, frei_dataloader.py:134-147)."""
     if res[0] != res[1]:
         raise LighthandError("crop: square output only (the reference passes [img_res, img_res])")
-    recs, scratch_floats, max_px = crop_descriptors(centers, scales, res, rots, pns)
+    recs, scratch_floats, max_wh = crop_descriptors(centers, scales, res, rots, pns)
     desc = descriptors_to_device(recs, images_u8.device)
     rot = torch.tensor([i for i, r in enumerate(recs) if r.rotated], dtype=torch.int32).to(images_u8.device)
-    return ops.frei_rgb_processing(images_u8, desc, int(res[0]), scratch_floats, max_px, rot_index=rot)
+    return ops.frei_rgb_processing(images_u8, desc, int(res[0]), scratch_floats, max_wh, rot_index=rot)
 
 
 def crop(img, center, scale, res, rot=0):

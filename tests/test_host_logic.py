@@ -115,7 +115,7 @@ def test_frei_crop_descriptors_follow_the_reference_bookkeeping():
     scales = rng.uniform(0.4, 1.8, n)
     rots = np.where(rng.uniform(size=n) < 0.5, 0.0, rng.uniform(-180, 180, n))
     pns = rng.uniform(0.6, 1.4, (n, 3))
-    recs, scratch, max_px = image_ops.crop_descriptors(centers, scales, [224, 224], rots, pns)
+    recs, scratch, max_wh = image_ops.crop_descriptors(centers, scales, [224, 224], rots, pns)
     off = 0
     for i in range(n):
         g = R.frei_crop_geometry(centers[i], float(scales[i]), [224, 224], float(rots[i]), (224, 224))
@@ -127,7 +127,7 @@ def test_frei_crop_descriptors_follow_the_reference_bookkeeping():
             want = R.cv2_invert_affine(R.cv2_rotation_matrix(((r.cw - 1) * 0.5, (r.ch - 1) * 0.5), float(rots[i]))).ravel()
             assert np.array_equal(np.array(list(r.iM)), want) and r.scratch_off == off
             off += 3 * (r.cw - 2 * r.pad) * (r.ch - 2 * r.pad)
-    assert scratch == off and max_px > 0
+    assert scratch == off and max_wh[0] > 0 and max_wh[1] > 0
     for pt in ([1, 1], [100.5, 30.25]):
         assert np.array_equal(image_ops.transform(pt, centers[0], scales[0], [224, 224], invert=1, rot=rots[1]),
                               R.frei_transform(pt, centers[0], scales[0], [224, 224], invert=1, rot=rots[1]))

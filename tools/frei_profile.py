@@ -23,4 +23,4 @@ for _ in range(3):
     rgb = ops.frei_rgb_processing(imgs, desc, 224, sfl, mpx, rot_index=rot)
     out = ops.resize_normalize_f32(rgb, (256, 256), chan_order=ops.LH_CHAN_BGR)
 torch.cuda.synchronize()
-print("rotated", sum(r.rotated for r in recs), "max_px", mpx, "scratch MB", sfl * 4 / 1e6)
+print("rotated", sum(r.rotated for r in recs), "max_wh", mpx, "scratch MB", sfl * 4 / 1e6)

@@ -92,7 +92,7 @@ def main():
     rot = torch.tensor([i for i, r in enumerate(recs) if r.rotated], dtype=torch.int32, device=dev)
     def frei_rgb(i):
         ops.check(lib.lh_frei_rgb_processing(fimgs[i].data_ptr(), 224 * 224 * 3, 224, 224, 224 * 3, desc.data_ptr(), N, 224,
-                                             rot.data_ptr(), rot.numel(), scratch.data_ptr(), mpx, rgb.data_ptr(),
+                                             rot.data_ptr(), rot.numel(), scratch.data_ptr(), mpx[0], mpx[1], rgb.data_ptr(),
                                              torch.cuda.current_stream().cuda_stream))
     frei_bytes = N * (224 * 224 * 3 + 224 * 224 * 12)
     rec("frei rgb_processing (rotate+resize)", timeit(frei_rgb, R), frei_bytes)
