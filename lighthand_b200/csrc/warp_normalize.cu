@@ -21,7 +21,7 @@ namespace lh {
 
 #ifdef LH_DEBUG_BOUNDS
 // compute-sanitizer is not available on the GPU pool: a debug build counts every shared-memory index of the
-// fast kernel that falls outside the staged window (tools/check_bounds.py reads the counter back)
+// fast kernel that falls outside the staged window (tests/check_bounds.py reads the counter back)
 __device__ unsigned long long g_lh_oob = 0ull;
 #define LH_BOUNDS(cond) do { if (!(cond)) atomicAdd(&g_lh_oob, 1ull); } while (0)
 #else

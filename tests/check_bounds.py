@@ -1,11 +1,11 @@
 #!/usr/bin/env python
-"""Bounds self-check of the fast warp kernel (compute-sanitizer is closed on the GPU pool).
-Build the debug library first:
+"""TEST INFRASTRUCTURE (uses the CPU oracle as the checker; not collected by pytest).
+Bounds self-check of the fast warp kernel (compute-sanitizer is closed on the GPU pool).  Build the debug library first:
     cd lighthand_b200/csrc && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC \
         -DLH_DEBUG_BOUNDS -c warp_normalize.cu -o /tmp/wn_dbg.o && \
     nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../variants_dbg.so build/capi.o build/heatmap.o \
-        build/metrics.o /tmp/wn_dbg.o build/pipeline.o -cudart static
-then  LIGHTHAND_B200_LIB=$PWD/variants_dbg.so python tools/check_bounds.py
+        build/metrics.o /tmp/wn_dbg.o build/pipeline.o build/frei_crop.o build/color_jitter.o -cudart static
+then  LIGHTHAND_B200_LIB=$PWD/variants_dbg.so python tests/check_bounds.py
 Sweeps rotations / scales / flips / crops leaving the image at several sizes and reports how many shared-memory
 indices fell outside the staged window (must be 0) and that the pixels still equal the CPU model."""
 import ctypes
