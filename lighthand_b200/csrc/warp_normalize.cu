@@ -522,16 +522,17 @@ __global__ void __launch_bounds__(kFThreads, LH_FAST_MINB) warp_pairs_kernel(con
                 w[i][0] = w[i][1] = w[i][2] = 0u;
                 if (g < bx.total) {
                     const int r = (int)((g * bx.inv) >> 20), k = g - r * bx.gpr;
+                    // byte offsets inside one image fit 32 bits (the launcher checks src_h * pitch < 2^31)
                     if (interior) {
-                        const uint32_t* rp = reinterpret_cast<const uint32_t*>(org + (long long)r * p.pitch) + 3 * k;
+                        const uint32_t* rp = reinterpret_cast<const uint32_t*>(org + (r * p.pitch + 12 * k));
                         w[i][0] = __ldg(rp); w[i][1] = __ldg(rp + 1); w[i][2] = __ldg(rp + 2);
                     } else {
                         const int y = bx.loy + r, bo = 3 * (bx.cx0 + 4 * k);
                         if (y >= 0 && y < p.sh) {
-                            const uint32_t* rp = reinterpret_cast<const uint32_t*>(img + (long long)y * p.pitch);
-                            if (bo >= 0 && bo < rowb) w[i][0] = __ldg(rp + (bo >> 2));
-                            if (bo + 4 >= 0 && bo + 4 < rowb) w[i][1] = __ldg(rp + (bo >> 2) + 1);
-                            if (bo + 8 >= 0 && bo + 8 < rowb) w[i][2] = __ldg(rp + (bo >> 2) + 2);
+                            const uint32_t* rp = reinterpret_cast<const uint32_t*>(img + (y * p.pitch + bo));
+                            if (bo >= 0 && bo < rowb) w[i][0] = __ldg(rp);
+                            if (bo + 4 >= 0 && bo + 4 < rowb) w[i][1] = __ldg(rp + 1);
+                            if (bo + 8 >= 0 && bo + 8 < rowb) w[i][2] = __ldg(rp + 2);
                         }
                     }
                 }
@@ -895,7 +896,8 @@ extern "C" int lh_warp_normalize(const uint8_t* src, int64_t src_img_stride, int
     } else {
         const bool stage = aligned16(src) && (src_pitch % 16 == 0) && (src_img_stride % 16 == 0);
         const bool words = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)src_pitch | (uintptr_t)src_img_stride) & 3u) == 0;
-        if (interp == LH_INTERP_CV2_U8 && words) {
+        const bool small = (long long)src_h * src_pitch < (1LL << 31);     // 32-bit byte offsets inside an image
+        if (interp == LH_INTERP_CV2_U8 && words && small) {
             if (!lut && mean_std) fma_coeffs(p, mean_std);
             // one launch addresses the output with 32-bit element indices: chunk the batch below 2^31 elements
             const long long per_img = 3LL * out_h * out_w;
