@@ -54,10 +54,10 @@ __device__ __forceinline__ uint32_t order_key(float v) {
 __device__ __forceinline__ int clamp_i(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
 __device__ __forceinline__ int sat_i32(double v) {
-    // cv::saturate_cast<int>(double) == cvRound (round-half-even) with saturation
-    if (!(v > -2147483648.0)) return (v != v) ? (int)0x80000000 : (int)0x80000000;
-    if (v >= 2147483647.0) return 0x7fffffff;
-    return __double2int_rn(v);
+    // cv::saturate_cast<int>(double) == cvRound (round-half-even) with saturation.  F2I.F64 saturates by itself
+    // (branch-free); only NaN needs the select (F2I gives 0, the reference path INT_MIN)
+    const int r = __double2int_rn(v);
+    return (v != v) ? (int)0x80000000 : r;
 }
 
 // OpenCV's in-place inversion of the forward 2x3 matrix (imgwarp.cpp; Appendix A step 1).
