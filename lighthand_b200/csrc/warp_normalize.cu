@@ -9,12 +9,16 @@
 // formed in double exactly like OpenCV, coordinates are quantised to 1/32 px with round-half-even,
 // and the uint8 result is (sum p*w + 2^14) >> 15 with w = 32*wx*wy  ==  (sum p*wx*wy + 512) >> 10.
 //
-// Layout: one CTA = one 32x32 output tile of one image, 256 threads, 4 consecutive x per thread.
-// The source footprint of the tile (a rotated rectangle) is bounded from the tile corners, its
-// bounding rows are staged into shared memory with 16-byte coalesced loads, and the four taps are
-// fetched from there as aligned 32-bit words + funnel shifts.  The uint8 result indexes a 3x256
-// float table (exact (v/255-mean)/std, optionally per image with the colour gain folded in), so
-// the normalisation costs no divisions.  Output: three 16-byte streaming stores per thread.
+// Kernels in this file (one C-ABI entry point, lh_warp_normalize, picks among them):
+//   warp_pairs_kernel    the fast uint8 path (LH_INTERP_CV2_U8, 4-byte aligned rows): record staging + IDP.4A,
+//                        described below at "Fast uint8 path" -- the kernel the benchmark runs
+//   resize_pairs_kernel  the fast ToTensor -> Resize -> Normalize path (LH_INTERP_TORCH), same structure
+//   warp_cv2_kernel      general fallback (unaligned rows, float32-weight mode): one CTA = one 32x32 output tile,
+//                        256 threads, 4 consecutive x per thread; the tile's bounding source rows are staged with
+//                        16-byte loads and the taps fetched as aligned words + funnel shifts; the uint8 result
+//                        indexes a 3x256 float table (exact (v/255-mean)/std, optionally per image with the colour
+//                        gain folded in); three 16-byte streaming stores per thread
+//   resize_torch_kernel  exact-operation-order resize (flip / gain / unaligned rows)
 #include "lh_common.cuh"
 
 namespace lh {
@@ -271,8 +275,9 @@ __global__ void __launch_bounds__(kWThreads) warp_cv2_kernel(const WarpParams p)
 // border; the two record formats are described at LH_REC4 below).  A bilinear tap pair of one source
 // row reaches the blend as the words { R[x] R[x+1] G[x] G[x+1] } and { B[x] B[x+1] - - }, so the
 // horizontal blend of a channel is one IDP.4A against the weight word (32-ax, ax, 0, 0) [<< 16 for G]
-// -- no byte unpacking, no funnel shifts, no per-pixel bounds test.  Lane = output column, so the 32 lanes of a tap load walk neighbouring
-// records (bank-conflict free up to the rotation) and every store instruction writes one 128-byte line.
+// -- no byte unpacking, no funnel shifts, no per-pixel bounds test.  Lane = output column, so the 32 lanes of
+// a tap load walk neighbouring records (bank-conflict free up to the rotation) and every store instruction
+// writes one 128-byte line.
 // The horizontal flip is folded into the coordinate tables exactly:
 //   X' = 32(sw-1) - X  in the 1/32-px fixed-point domain  <=>  X0' = 1024(sw-1) + 31 - X0, adelta' = -adelta.
 // Normalisation: NORM 0 none (0..255), 1 single FMA v*a+b, 2 exact table (torch's three roundings).
@@ -280,8 +285,8 @@ __global__ void __launch_bounds__(kWThreads) warp_cv2_kernel(const WarpParams p)
 // Record format of the staged window.  LH_REC4 = 1 (default): one 4-byte record {R G B x} per source pixel -- a tap
 // row is two LDS.32 (x, x+1) re-paired by two PRMT into the words the IDP.4A blend wants; half the shared memory of
 // the 8-byte pair records {R[x] R[x+1] G[x] G[x+1] | B[x] B[x+1] - -} (LH_REC4 = 0: one LDS.64 per tap row, no PRMT),
-// so 12 instead of 8 CTAs fit an SM.  Measured on B200 (C2 mix, 256 images): 59.8 us against 68.4 us; the kernel is
-// bound by tiles in flight x tile latency, not by instruction count.
+// so 12 instead of 8 CTAs fit an SM.  Measured on B200 (C2 mix, 256 images): 59.8 us against 68.4 us -- with pair
+// records the kernel was bound by tiles in flight x tile latency; at 12 CTAs / SM it is issue-bound.
 #ifndef LH_REC4
 #define LH_REC4 1
 #endif
