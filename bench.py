@@ -223,6 +223,27 @@ def load_traffic(kernel_key):
     return None
 
 
+def bind_to_gpu_cpus(local):
+    """Multi-GPU runs: pin this rank to the CPU cores NVML reports as local to its GPU, so the pinned host buffers of
+    the e2e leg (first touch) sit on the GPU's NUMA node.  Best effort: any failure leaves the affinity untouched."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        allowed = os.sched_getaffinity(0)
+        cpus = {i for i in range(ncpu) if (int(words[i // 64]) >> (i % 64)) & 1} & allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
     wl = WORKLOADS[args.workload]
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -247,6 +268,7 @@ def run_ours(args):
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_cpus(local) if world > 1 else None     # pinned e2e buffers land next to this rank's GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -422,6 +444,7 @@ def run_ours(args):
         "two_stream": overlap,
         "cpu_baseline": cpu,
         "e2e": e2e,
+        "host_affinity_cores": numa,
         "gpu_launches": pipe.launches_per_step * K,
         "clocks": clocks,
         "check": {"pck@0.2": metrics["pck"], "epe_px": metrics["epe"], "loss": metrics["loss"], "n_images": metrics["n_images"]},
@@ -450,6 +473,7 @@ def run_eval_sweep(args):
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_cpus(local) if world > 1 else None     # pinned e2e buffers land next to this rank's GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, S, H, sigma, total = wl["batch"], wl["S"], wl["H"], wl["sigma"], wl["total"]
