@@ -291,10 +291,12 @@ __global__ void __launch_bounds__(kWThreads) warp_cv2_kernel(const WarpParams p)
 #define LH_REC4 1
 #endif
 #ifndef LH_FAST_MAXPOS
-#define LH_FAST_MAXPOS (LH_REC4 ? 3328 : 3200)
+#define LH_FAST_MAXPOS (LH_REC4 ? 3072 : 3200)
 #endif
-constexpr int kRecWords = LH_FAST_MAXPOS;   // LH_REC4 = 1: 4-byte records per CTA (3328 = 13 KB: a 32x32 tile rotated 45
-                                            // degrees at unit scale touches 50 x 48 source pixels -> pitch 60 x 49 rows)
+constexpr int kRecWords = LH_FAST_MAXPOS;   // LH_REC4 = 1: 4-byte records per CTA (3072 = 12 KB: a 32x32 tile rotated 45
+                                            // degrees at unit scale touches 50 x 48 source pixels -> pitch 60 x 49 rows
+                                            // = 2940; 12 CTAs then fit the 164 KB shared-memory carve-out, which leaves
+                                            // 92 KB of L1 instead of 60 KB: -1 %)
 #if !LH_REC4
 constexpr int kMaxPos = LH_FAST_MAXPOS;     // LH_REC4 = 0: 8-byte pair records per CTA (3200 = 25 KB)
 #endif
