@@ -18,29 +18,22 @@ from ..ops import LighthandError
 
 
 def get_transform(center, scale, res, rot=0):
-    """src/utils/image_ops.py:59-83."""
-    h = 200 * scale
-    t = np.zeros((3, 3))
-    t[0, 0] = float(res[1]) / h
-    t[1, 1] = float(res[0]) / h
-    t[0, 2] = res[1] * (-float(center[0]) / h + .5)
-    t[1, 2] = res[0] * (-float(center[1]) / h + .5)
-    t[2, 2] = 1
-    if not rot == 0:
-        rot = -rot
-        rot_mat = np.zeros((3, 3))
-        rot_rad = rot * np.pi / 180
-        sn, cs = np.sin(rot_rad), np.cos(rot_rad)
-        rot_mat[0, :2] = [cs, -sn]
-        rot_mat[1, :2] = [sn, cs]
-        rot_mat[2, 2] = 1
-        t_mat = np.eye(3)
-        t_mat[0, 2] = -res[1] / 2
-        t_mat[1, 2] = -res[0] / 2
-        t_inv = t_mat.copy()
-        t_inv[:2, 2] *= -1
-        t = np.dot(t_inv, np.dot(rot_mat, np.dot(t_mat, t)))
-    return t
+    """src/utils/image_ops.py:59-83: the 3x3 map from image pixels to the res x res crop of a box of side
+    200 * scale around ``center``, optionally rotated about the crop centre.  Same float64 operations in the same
+    order as the reference (the integer window corners of ``crop`` depend on the last bit)."""
+    side = 200 * scale
+    t = np.array([[float(res[1]) / side, 0.0, res[1] * (-float(center[0]) / side + .5)],
+                  [0.0, float(res[0]) / side, res[0] * (-float(center[1]) / side + .5)],
+                  [0.0, 0.0, 1.0]])
+    if rot == 0:
+        return t
+    angle = -rot * np.pi / 180            # the crop rotates against the image
+    sn, cs = np.sin(angle), np.cos(angle)
+    spin = np.array([[cs, -sn, 0.0], [sn, cs, 0.0], [0.0, 0.0, 1.0]])
+    to_centre, back = np.eye(3), np.eye(3)
+    to_centre[0, 2], to_centre[1, 2] = -res[1] / 2, -res[0] / 2
+    back[0, 2], back[1, 2] = -to_centre[0, 2], -to_centre[1, 2]
+    return np.dot(back, np.dot(spin, np.dot(to_centre, t)))
 
 
 def transform(pt, center, scale, res, invert=0, rot=0):
