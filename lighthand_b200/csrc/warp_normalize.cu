@@ -417,6 +417,57 @@ __device__ __forceinline__ void warp_rows(const WarpParams& p, const TileBox& bx
 #define LH_STAGE_DEPTH 3
 #endif
 constexpr int kStageDepth = LH_STAGE_DEPTH;   // groups of 4 records whose loads a thread keeps in flight together
+#if LH_REC4
+// Stage the footprint as 4-byte records.  A group = 4 source pixels = 3 words -> 4 records {R G B x} (byte 3 is
+// don't-care: it only ever meets a zero weight), one STS.128 per group; the loads of up to kStageDepth groups of a
+// thread are issued before the first conversion (one global round trip per tile).  Byte offsets inside one image
+// fit 32 bits (the launcher checks src_h * pitch < 2^31).
+template <bool INTERIOR>
+__device__ __forceinline__ void stage_rec4(const WarpParams& p, const TileBox& bx, uint32_t* s_w, const uint8_t* img,
+                                           const uint8_t* org, int rowb, int tid) {
+    for (int g0 = tid; g0 < bx.total; g0 += kStageDepth * kFThreads) {
+        uint32_t w[kStageDepth][3];
+#pragma unroll
+        for (int i = 0; i < kStageDepth; ++i) {
+            const int g = g0 + i * kFThreads;
+            w[i][0] = w[i][1] = w[i][2] = 0u;
+            if (g < bx.total) {
+                const int r = (int)((g * bx.inv) >> 20), k = g - r * bx.gpr;
+                if (INTERIOR) {
+                    const uint32_t* rp = reinterpret_cast<const uint32_t*>(org + (r * p.pitch + 12 * k));
+                    w[i][0] = __ldg(rp); w[i][1] = __ldg(rp + 1); w[i][2] = __ldg(rp + 2);
+                } else {
+                    const int y = bx.loy + r, bo = 3 * (bx.cx0 + 4 * k);
+                    if (y >= 0 && y < p.sh) {
+                        const uint32_t* rp = reinterpret_cast<const uint32_t*>(img + (y * p.pitch + bo));
+                        if (bo >= 0 && bo < rowb) w[i][0] = __ldg(rp);
+                        if (bo + 4 >= 0 && bo + 4 < rowb) w[i][1] = __ldg(rp + 1);
+                        if (bo + 8 >= 0 && bo + 8 < rowb) w[i][2] = __ldg(rp + 2);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kStageDepth; ++i) {
+            const int g = g0 + i * kFThreads;
+            if (g >= bx.total) continue;
+            const int r = (int)((g * bx.inv) >> 20), k = g - r * bx.gpr;
+            const uint32_t w0 = w[i][0], w1 = w[i][1], w2 = w[i][2];
+            uint32_t px[4] = {w0, __byte_perm(w0, w1, 0x0543), __byte_perm(w1, w2, 0x0432), w2 >> 8};
+            if (!INTERIOR) {
+                const int y = bx.loy + r, x = bx.cx0 + 4 * k;
+                const bool yin = (y >= 0) & (y < p.sh);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)     // pixels outside the image are the constant border 0
+                    if (!(yin && (x + q >= 0) && (x + q < p.sw))) px[q] = 0u;
+            }
+            LH_BOUNDS(r >= 0 && r < bx.nrows && k >= 0 && 4 * k + 3 < bx.pitch && r * bx.pitch + 4 * k + 3 < kRecWords);
+            *reinterpret_cast<uint4*>(s_w + r * bx.pitch + 4 * k) = make_uint4(px[0], px[1], px[2], px[3]);
+        }
+    }
+}
+#endif
+
 template <int NORM>
 __global__ void __launch_bounds__(kFThreads, LH_FAST_MINB) warp_pairs_kernel(const WarpParams p) {
 #if LH_REC4
@@ -518,50 +569,9 @@ __global__ void __launch_bounds__(kFThreads, LH_FAST_MINB) warp_pairs_kernel(con
         const uint8_t* org = img + (long long)bx.loy * p.pitch + 3 * bx.cx0;
         const int rowb = 3 * p.sw;
 #if LH_REC4
-        // a group = 4 source pixels = 3 words -> 4 records {R G B x} (byte 3 is don't-care: it only ever meets a zero
-        // weight); one STS.128 per group
-        uint32_t* const s_w = reinterpret_cast<uint32_t*>(s_rec);
-        for (int g0 = tid; g0 < bx.total; g0 += kStageDepth * kFThreads) {
-            uint32_t w[kStageDepth][3];
-#pragma unroll
-            for (int i = 0; i < kStageDepth; ++i) {
-                const int g = g0 + i * kFThreads;
-                w[i][0] = w[i][1] = w[i][2] = 0u;
-                if (g < bx.total) {
-                    const int r = (int)((g * bx.inv) >> 20), k = g - r * bx.gpr;
-                    // byte offsets inside one image fit 32 bits (the launcher checks src_h * pitch < 2^31)
-                    if (interior) {
-                        const uint32_t* rp = reinterpret_cast<const uint32_t*>(org + (r * p.pitch + 12 * k));
-                        w[i][0] = __ldg(rp); w[i][1] = __ldg(rp + 1); w[i][2] = __ldg(rp + 2);
-                    } else {
-                        const int y = bx.loy + r, bo = 3 * (bx.cx0 + 4 * k);
-                        if (y >= 0 && y < p.sh) {
-                            const uint32_t* rp = reinterpret_cast<const uint32_t*>(img + (y * p.pitch + bo));
-                            if (bo >= 0 && bo < rowb) w[i][0] = __ldg(rp);
-                            if (bo + 4 >= 0 && bo + 4 < rowb) w[i][1] = __ldg(rp + 1);
-                            if (bo + 8 >= 0 && bo + 8 < rowb) w[i][2] = __ldg(rp + 2);
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < kStageDepth; ++i) {
-                const int g = g0 + i * kFThreads;
-                if (g >= bx.total) continue;
-                const int r = (int)((g * bx.inv) >> 20), k = g - r * bx.gpr;
-                const uint32_t w0 = w[i][0], w1 = w[i][1], w2 = w[i][2];
-                uint32_t px[4] = {w0, __byte_perm(w0, w1, 0x0543), __byte_perm(w1, w2, 0x0432), w2 >> 8};
-                if (!interior) {
-                    const int y = bx.loy + r, x = bx.cx0 + 4 * k;
-                    const bool yin = (y >= 0) & (y < p.sh);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)     // pixels outside the image are the constant border 0
-                        if (!(yin && (x + q >= 0) && (x + q < p.sw))) px[q] = 0u;
-                }
-                LH_BOUNDS(r >= 0 && r < bx.nrows && k >= 0 && 4 * k + 3 < bx.pitch && r * bx.pitch + 4 * k + 3 < kRecWords);
-                *reinterpret_cast<uint4*>(s_w + r * bx.pitch + 4 * k) = make_uint4(px[0], px[1], px[2], px[3]);
-            }
-        }
+        // the whole window inside the image (the common case) takes a loop without predicates
+        if (interior) stage_rec4<true>(p, bx, reinterpret_cast<uint32_t*>(s_rec), img, org, rowb, tid);
+        else          stage_rec4<false>(p, bx, reinterpret_cast<uint32_t*>(s_rec), img, org, rowb, tid);
 #else
         for (int g0 = tid; g0 < bx.total; g0 += kStageDepth * kFThreads) {
             uint32_t w[kStageDepth][4];
