@@ -106,3 +106,24 @@ def test_against_the_reference_fixture():
     par = g["big_par"][0]
     c = image_ops.crop(g["big"][0], par[:2], float(par[2]), [224, 224], rot=float(par[3]))
     np.testing.assert_allclose(c.cpu().numpy(), g["crops"][0], rtol=0, atol=5e-4)
+
+
+def test_empty_batch_and_unrotated_only_batch():
+    """N = 0 is a no-op; a batch without any rotated sample needs no scratch canvas and no rotate launch."""
+    from lighthand_b200 import ops
+    from lighthand_b200.datasets import frei_dataloader as F
+    from lighthand_b200.utils import image_ops
+    empty = torch.zeros((0, 224, 224, 3), dtype=torch.uint8, device="cuda")
+    out = image_ops.crop_batch(empty, [], [], [224, 224], [])
+    assert out.shape == (0, 3, 224, 224)
+    img, j2d, hm = F.frei_batch(empty, np.zeros((0, 21, 3)), [], [])
+    assert img.shape == (0, 3, 256, 256) and j2d.shape == (0, 21, 2) and hm.shape == (0, 21, 64, 64)
+    assert ops.color_jitter_normalize(torch.zeros((0, 3, 8, 8), device="cuda"), []).shape == (0, 3, 8, 8)
+    imgs, centers, scales, _, pns = _inputs(4, 224, 224, 36)
+    rots = np.zeros(4)
+    recs, scratch, max_wh = image_ops.crop_descriptors(centers, scales, [224, 224], rots, pns)
+    assert scratch == 0 and max_wh == (0, 0)
+    got = F.rgb_processing(torch.from_numpy(imgs).cuda(), centers, scales, rots, pns).cpu().numpy()
+    for i in range(4):
+        want = R.frei_rgb_processing(imgs[i], centers[i], float(scales[i]), 0.0, pns[i])
+        np.testing.assert_allclose(got[i], want, rtol=0, atol=2e-6)
