@@ -430,6 +430,7 @@ def run_ours(args):
                    "launch": "pre-marshalled C-ABI calls, 2 kernels/step (K1; K2+K3+K4+K5 fused)", "normalise": "one FMA per value (<=2 ulp of torch)"},
         "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
+                     "frac_of_nominal_8000GBps": achieved / 8000.0,      # north_star quotes the nominal HBM3e figure too
                      "traffic": load_traffic("warp_pairs" if dom[0] == "warp_normalize" else "heatmap_vec") if args.workload == "C2" and not args.batch else None,
                      "traffic_note": "dram__bytes_read+write per launch, ncu --set full (profiles/r01_final_traffic.json); below the algorithmic bytes because part of the output is still dirty in the 126 MB L2 when the kernel ends",
                      "peak_source": peak_src,
