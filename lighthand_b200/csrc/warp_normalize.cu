@@ -791,9 +791,13 @@ __global__ void __launch_bounds__(kFThreads, 12) resize_pairs_kernel(const WarpP
         const uint32_t* q0 = s_rec + s_r0[r] * pitch + cx;
         const uint32_t* q1 = s_rec + s_r1[r] * pitch + cx;
         const uint32_t a0 = q0[0], a1 = q0[1], b0 = q1[0], b1 = q1[1];
+        // byte -> float without the quarter-rate I2F.U8: PRMT the byte under the exponent of 2^23, subtract 2^23 (exact)
+        auto bytef = [](uint32_t w_, int k_) {
+            return __uint_as_float(__byte_perm(w_, 0x4B000000u, 0x7650 | k_)) - 8388608.0f;
+        };
         auto lerp2 = [&](int sh_) {
-            const float p00 = (float)((a0 >> sh_) & 0xffu), p01 = (float)((a1 >> sh_) & 0xffu);
-            const float p10 = (float)((b0 >> sh_) & 0xffu), p11 = (float)((b1 >> sh_) & 0xffu);
+            const float p00 = bytef(a0, sh_ >> 3), p01 = bytef(a1, sh_ >> 3);
+            const float p10 = bytef(b0, sh_ >> 3), p11 = bytef(b1, sh_ >> 3);
             const float top = fmaf(lx1, p01, lx0 * p00), bot = fmaf(lx1, p11, lx0 * p10);
             return fmaf(ly1, bot, ly0 * top);
         };
