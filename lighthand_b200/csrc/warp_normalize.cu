@@ -19,7 +19,11 @@
 //                        indexes a 3x256 float table (exact (v/255-mean)/std, optionally per image with the colour
 //                        gain folded in); three 16-byte streaming stores per thread
 //   resize_torch_kernel  exact-operation-order resize (flip / gain / unaligned rows)
+#include <cstdlib>
+#include <cstring>
+
 #include "lh_common.cuh"
+#include "warp_params.cuh"
 
 namespace lh {
 
@@ -46,22 +50,6 @@ constexpr int kTile = 32;
 constexpr int kWThreads = 256;
 constexpr int kStageBytes = 24 * 1024;
 
-struct WarpParams {
-    const uint8_t* src;
-    long long img_stride;
-    int sh, sw, pitch;
-    const double* M;
-    const uint8_t* flip;
-    const double* gain;
-    const float* lut;
-    int lut_per_image;
-    int normalise;
-    float mean[3], stdv[3];
-    int chan_order, layout;
-    float* dst;
-    int N, oh, ow;
-    int vec_store;
-};
 
 __device__ __forceinline__ uint32_t lds32(const uint8_t* base, int word) {
     return reinterpret_cast<const uint32_t*>(base)[word];
@@ -828,6 +816,11 @@ __global__ void norm_lut_kernel(const double* gain, int tables, int normalise, f
 
 using namespace lh;
 
+static bool k1_force_records() {
+    static const bool v = [] { const char* e = getenv("LH_K1"); return e && !strcmp(e, "records"); }();
+    return v;
+}
+
 // v*a + b with a = 1/(255 std), b = -mean/std, rounded once from double; stored in p.mean / p.stdv
 static void fma_coeffs(WarpParams& p, const float* mean_std) {
     for (int i = 0; i < 3; ++i) {
@@ -930,6 +923,14 @@ extern "C" int lh_warp_normalize(const uint8_t* src, int64_t src_img_stride, int
                 q.src = src + (long long)n0 * src_img_stride; q.M = fwd_affine + (long long)n0 * 6;
                 q.flip = flip ? flip + n0 : nullptr; q.dst = dst + (long long)n0 * per_img; q.N = nc;
                 if (lut && q.lut_per_image) q.lut = lut + (size_t)n0 * 768;
+                // TMA-staged persistent kernel first (16-byte aligned base / pitch / image stride, no per-image
+                // table); LH_K1=records in the environment keeps the record-staging kernel for A/B measurements
+                const int norm = lut ? 2 : (mean_std ? 1 : 0);
+                if (!k1_force_records()) {
+                    const int rc = launch_warp_tma(q, norm, st);
+                    if (rc == LH_OK) continue;
+                    if (rc != kTmaNotApplicable) return rc;
+                }
                 dim3 fgrid((out_w + kTileW - 1) / kTileW, (out_h + kTileH - 1) / kTileH, nc);
                 if (lut)           warp_pairs_kernel<2><<<fgrid, kFThreads, 0, st>>>(q);
                 else if (mean_std) warp_pairs_kernel<1><<<fgrid, kFThreads, 0, st>>>(q);
