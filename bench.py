@@ -66,27 +66,6 @@ def synth_host(n, S, seed):
 # ------------------------------------------------------------------------------------------------
 # CPU path: the oracle port of the reference, one process per host core, each on its own batch
 # ------------------------------------------------------------------------------------------------
-def _cpu_pass(R, torch, data, S, H, sigma, train):
-    """One pass of the reference's per-iteration work over one host batch (the loops the reference runs:
-    per-sample warp + normalise and generate_target, then loss[/backward], decode, PCK, EPE)."""
-    imgs, joints, bbox, scale, rot, flip, pred = data
-    n = imgs.shape[0]
-    stride = S / H
-    tgt = []
-    for i in range(n):
-        R.warp_normalize_sample(imgs[i], bbox[i], bool(flip[i]), float(scale[i]), float(rot[i]), (S, S))
-        tgt.append(R.generate_target(joints[i], 21, (H, H), (stride, stride), sigma)[0])
-    tgt = np.stack(tgt)
-    if train:
-        R.joints_mse_loss_and_grad(pred, tgt)
-    else:
-        float(R.joints_mse_loss(pred, tgt))
-    coords, _ = R.get_max_preds(pred)
-    coords = coords * stride
-    R.pck_2d(coords, joints, 0.2, "proportion")
-    R.epe_train(coords, joints)
-
-
 def _cpu_worker(args):
     wid, S, H, sigma, train, n, warm, steps, t_start = args
     import torch
@@ -96,25 +75,29 @@ def _cpu_worker(args):
         cv2.setNumThreads(1)
     except Exception:
         pass
-    from oracle import restate as R
+    from oracle import reference_arm, restate as R
+    ns, _kind = reference_arm.load()
+    cpu_pass = reference_arm.make_pass(ns, R, torch)
     d = synth_host(n, S, 1000 + wid)
     pred = np.random.default_rng(wid).standard_normal((n, 21, H, H)).astype(np.float32)
     data = (*d, pred)
     for _ in range(warm):
-        _cpu_pass(R, torch, data, S, H, sigma, train)
+        cpu_pass(data, S, H, sigma, train)
     while time.time() < t_start:          # common start line
         time.sleep(0.001)
     t0 = time.perf_counter()
     for _ in range(steps):
-        _cpu_pass(R, torch, data, S, H, sigma, train)
+        cpu_pass(data, S, H, sigma, train)
     return time.perf_counter() - t0
 
 
 def cpu_throughput(wl, steps, warmup, sample_n=32, max_workers=64):
-    """images/s of the oracle port with one worker process per host core (fork; call before CUDA init)."""
+    """images/s of the reference's CPU path with one worker process per host core (fork; call before CUDA init):
+    the reference's own functions from baseline/_ref (kind "reference"), else the oracle port (kind "port")."""
     import multiprocessing as mp
     import torch  # noqa: F401  (imported before the fork so the workers share the pages; CUDA is not touched)
-    from oracle import restate  # noqa: F401
+    from oracle import reference_arm, restate  # noqa: F401
+    ns, kind = reference_arm.load()          # imported once here: the forked workers share it
     cores = os.cpu_count() or 1
     workers = max(1, min(cores, max_workers))
     ctx = mp.get_context("fork")
@@ -123,9 +106,12 @@ def cpu_throughput(wl, steps, warmup, sample_n=32, max_workers=64):
     with ctx.Pool(workers) as pool:
         times = pool.map(_cpu_worker, jobs)
     t = max(times)
-    return dict(value=workers * sample_n * steps / t, seconds=t, workers=workers, cores_online=cores,
+    what = ("the reference's own functions (generate_patch_image, ToTensor+Normalize, generate_target, JointsMSELoss"
+            "[+backward], get_max_preds, PCK_2d_loss, EPE_train) from baseline/_ref" if kind == "reference"
+            else "oracle port of the reference's numpy/cv2/torch-CPU loops")
+    return dict(value=workers * sample_n * steps / t, seconds=t, workers=workers, cores_online=cores, kind=kind,
                 sample=f"{workers} worker processes x {steps} passes over a {sample_n}-image batch of the same workload "
-                       f"(oracle port of the reference's numpy/cv2/torch-CPU loops, 1 thread each)")
+                       f"({what}, 1 thread each)")
 
 
 def run_reference_arm(args):
@@ -133,16 +119,16 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 3))
-    # bound the run: one pass over 32 images costs ~0.3-1 s per worker
-    steps = min(steps, 20)
+    # a step of this arm = one pass of every worker over its 32-image batch (0.3-1 s); bound the run to a few minutes
+    steps, warmup = max(1, min(args.steps, 40)), max(1, min(args.warmup, 10))
     r = cpu_throughput(wl, steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": 1e3 * r["seconds"] / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "global_batch": r["workers"] * 32, "parallelism": f"cpu x{r['workers']} processes"},
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["workers"], "kind": "port", "sample": r["sample"]},
+        "config": {"workload": wl["desc"], "global_batch": r["workers"] * 32, "batch_per_gpu": wl["batch"],
+                   "parallelism": f"cpu x{r['workers']} processes, 32-image batches (steps/warm-up capped at 40/10: one step is ~0.5 s of every core)"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["workers"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -244,6 +230,50 @@ def bind_to_gpu_cpus(local):
     return None
 
 
+def _max_over_ranks(x, dev, world, dist):
+    if world == 1:
+        return float(x)
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _gather_ranks(x, dev, world, dist):
+    if world == 1:
+        return [float(x)]
+    import torch
+    t = torch.zeros(world, dtype=torch.float64, device=dev)
+    t[dist.get_rank()] = x
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [float(v) for v in t.tolist()]
+
+
+def h2d_ceiling(nbytes, dev, world, dist, reps=12):
+    """Plain pinned-host -> device copies of one step's input bytes, all ranks at once: the PCIe / host-memory ceiling the
+    e2e number is measured against (GB/s of this rank; the caller gathers)."""
+    import torch
+    src = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    for t in src:
+        t.fill_(7)
+    dst = [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+    st = torch.cuda.Stream(dev)
+    with torch.cuda.stream(st):
+        for i in range(2):
+            dst[i].copy_(src[i], non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(st):
+        for i in range(reps):
+            dst[i % 2].copy_(src[i % 2], non_blocking=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return nbytes * reps / dt / 1e9
+
+
 def run_ours(args):
     wl = WORKLOADS[args.workload]
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -257,7 +287,7 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_throughput(wl, steps=args.cpu_steps, warmup=1)
-        cpu = {"value": r["value"], "unit": UNIT, "cores": r["workers"], "kind": "port", "sample": r["sample"],
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["workers"], "kind": r["kind"], "sample": r["sample"],
                "seconds": r["seconds"]}
 
     import torch
@@ -269,24 +299,29 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     numa = bind_to_gpu_cpus(local) if world > 1 else None     # pinned e2e buffers land next to this rank's GPU
+    comm = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        from lighthand_b200.distributed import metric_comm
+        comm = metric_comm()          # own NCCL communicator through the C ABI; its first collective is paid here
 
     # ---- inputs resident in HBM: a ring of R distinct batches (> L2 in total) ------------------------
+    # data are a function of the GLOBAL batch index (rank * ring + r): a rank's ring is a slice of one data set
     ring = max(2, args.ring)
     pipe = HeatmapPipeline(B, (S, S), (S, S), (H, H), sigma=sigma, train=train, materialize_target=args.materialize_target,
                            device=dev)
     stride = S / H
     sets, host_sets = [], []
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
     for r_i in range(ring):
-        imgs, joints, bbox, scale, rot, flip = synth_host(B, S, seed=(1234 + rank) * 100 + r_i)
+        gb = rank * ring + r_i
+        imgs, joints, bbox, scale, rot, flip = synth_host(B, S, seed=123400 + gb)
         trans, _ = batch_patch_matrices(bbox, flip, scale, rot, (S, S), (S, S))
         M = np.ascontiguousarray(trans.astype(np.float64))
         fl = np.ascontiguousarray(flip.astype(np.uint8))
         d_imgs = torch.from_numpy(imgs).to(dev)
         d_M, d_fl, d_j = torch.from_numpy(M).to(dev), torch.from_numpy(fl).to(dev), torch.from_numpy(joints).to(dev)
         tgt, _ = ops.gen_targets(d_j, (H, H), (stride, stride), sigma, want_weight=False)
+        g = torch.Generator(device=dev).manual_seed(99000 + gb)
         d_pred = tgt + 0.1 * torch.randn(tgt.shape, device=dev, generator=g)       # pred = target + noise
         del tgt
         sets.append(pipe.prepare(d_imgs, d_M, d_j, d_pred, flip=d_fl))
@@ -299,67 +334,86 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
 
-    K, W = args.steps, max(3, args.warmup)
+    def reduce_metrics():
+        if comm is not None:
+            comm.all_reduce([pipe.meter.counts, pipe.meter.sums])
+
+    K, W = max(1, args.steps), max(3, args.warmup)
+    # repetitions of the K-step region: the driver's K = 20 is a 2 ms region, far too short for a clock sample or
+    # for one scheduling hiccup to average out; >= ~250 ms in total, the MEDIAN repetition is reported
+    est_ms = 0.11 * K * (B * S * S) / (256 * 256 * 256)
+    reps = int(min(400, max(5, np.ceil(250.0 / max(est_ms, 1e-3))))) if args.repeats <= 0 else args.repeats
+
+    # ---- warm-up: W serial steps, W overlapped steps, one metric all-reduce ----------------------------
     for i in range(W):
         sets[i % ring].launch()
+    sets[0].launch_data()
+    for i in range(W):
+        sets[(i + 1) % ring].launch_data()
+        sets[i % ring].launch_loss()
+    sets[W % ring].launch_loss()
+    reduce_metrics()
     torch.cuda.synchronize()
-    pipe.reset_metrics()
 
-    # ---- timed region: K steps, CUDA events on the launching stream, metric all-reduce inside ------------
-    # two events per step: before K1 and between the two launches; the fused pass of step i ends where step
-    # i+1 begins (one more event closes the last step)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
-    ev_last = torch.cuda.Event(enable_timing=True)
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    barrier()
+
+    # ---- timed region A (value): the pipelined loop -- data stage of batch i+1 on the data stream while the loss
+    # stage of batch i runs on the main stream; K data stages + K loss stages + the metric all-reduce per repetition --
+    t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ar0, ar1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ov_ms, ar_us = [], []
+    sets[0].launch_data()                                  # prologue of the software pipeline (batch 0's data stage)
     torch.cuda.synchronize()
-    t_start.record()
-    for i in range(K):
-        sets[i % ring].launch(events=ev[i])
-    ev_last.record()
-    if world > 1:
-        from lighthand_b200.distributed import all_reduce_metrics
-        all_reduce_metrics([pipe.meter.counts, pipe.meter.sums])
-    t_end.record()
+    for rep in range(reps):
+        pipe.reset_metrics()
+        barrier()
+        torch.cuda.synchronize()
+        t0e.record()
+        for i in range(K):
+            sets[(i + 1) % ring].launch_data()             # data stage of the next batch (runs ahead)
+            sets[i % ring].launch_loss()                   # loss stage of the current batch
+        ar0.record()
+        reduce_metrics()
+        ar1.record()
+        t1e.record()
+        torch.cuda.synchronize()
+        barrier()
+        ov_ms.append(_max_over_ranks(t0e.elapsed_time(t1e), dev, world, dist))
+        ar_us.append(1e3 * ar0.elapsed_time(ar1))
+        # the K+1-th data stage issued above belongs to the next repetition's first loss stage
+    sets[K % ring].launch_loss()                           # drain the pipeline
     torch.cuda.synchronize()
-    barrier()
+    metrics_ov = pipe.meter.result()                       # all-reduced totals of the last repetition (+ the drain step)
+
+    # ---- timed region B: the same K steps serially on one stream, one event between the two launches: per-kernel
+    # durations for the roofline (kernels that overlap cannot be timed apart) --------------------------------
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
+    ev_last = torch.cuda.Event(enable_timing=True)
+    ser_ms, k1s, fus = [], [], []
+    reps_b = max(3, reps // 4)
+    for rep in range(reps_b):
+        pipe.reset_metrics()
+        barrier()
+        torch.cuda.synchronize()
+        t0e.record()
+        for i in range(K):
+            sets[i % ring].launch(events=ev[i])
+        ev_last.record()
+        reduce_metrics()
+        t1e.record()
+        torch.cuda.synchronize()
+        barrier()
+        ser_ms.append(_max_over_ranks(t0e.elapsed_time(t1e), dev, world, dist))
+        k1s.append(float(np.mean([e[0].elapsed_time(e[1]) for e in ev])))
+        fus.append(float(np.mean([ev[i][1].elapsed_time(ev[i + 1][0] if i + 1 < K else ev_last) for i in range(K)])))
     clocks = sampler.stop() if rank == 0 else None
-    ms = t_start.elapsed_time(t_end)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    # ---- optional: the two launches on two streams (they touch disjoint data) ---------------------------
-    overlap = None
-    if args.overlap:
-        sa, sb = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        snap = (pipe.meter.counts.clone(), pipe.meter.sums.clone())
-        cur = torch.cuda.current_stream(dev)
-        for rep in range(2):                      # first pass warms the streams up
-            barrier()
-            torch.cuda.synchronize()
-            o0.record()
-            sa.wait_stream(cur); sb.wait_stream(cur)
-            for i in range(K):
-                sets[i % ring].launch_split(sa.cuda_stream, sb.cuda_stream)
-            cur.wait_stream(sa); cur.wait_stream(sb)
-            o1.record()
-            torch.cuda.synchronize()
-        oms = o0.elapsed_time(o1)
-        if world > 1:
-            t = torch.tensor([oms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            oms = float(t.item())
-        overlap = {"value": world * B * K / (oms * 1e-3), "unit": UNIT, "ms_per_step": oms / K,
-                   "note": "K1 and the fused pass on two streams (disjoint data): data stage of batch i+1 overlaps the loss stage of batch i"}
-        pipe.meter.counts.copy_(snap[0]); pipe.meter.sums.copy_(snap[1])
-    metrics = pipe.metrics(all_reduce=False)
-    k1_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
-    fused_ms = float(np.mean([ev[i][1].elapsed_time(ev[i + 1][0] if i + 1 < K else ev_last) for i in range(K)]))
+    metrics = pipe.meter.result()                          # all-reduced totals of the last serial repetition
+    ms = float(np.median(ov_ms))
+    ms_serial = float(np.median(ser_ms))
+    per_rank_ms = _gather_ranks(float(np.median(ov_ms)), dev, world, dist)
+    k1_ms, fused_ms = float(np.median(k1s)), float(np.median(fus))
     value = world * B * K / (ms * 1e-3)
 
     # ---- e2e: host buffers through the C-ABI context, double-buffered, copies inside the timed region -------
@@ -376,7 +430,7 @@ def run_ours(args):
             d = hp.pinned(fl.shape, np.uint8); d[...] = fl
             pinned.append((a, b, c, d))
         outs = [hp.new_outputs(), hp.new_outputs()]
-        Ke = max(4, min(K, args.e2e_steps))
+        Ke = max(4, min(max(K, 50), args.e2e_steps))
         def run_e2e(n_steps):
             pend = None
             for i in range(n_steps):
@@ -388,26 +442,32 @@ def run_ours(args):
             hp.wait(pend[0])
         run_e2e(4)
         hp.reset_metrics()
-        barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        run_e2e(Ke)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        e2e_t = []
+        for rep in range(3):
+            barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            run_e2e(Ke)
+            torch.cuda.synchronize()
+            e2e_t.append(_max_over_ranks(time.perf_counter() - t0, dev, world, dist))
+        dt = float(np.median(e2e_t))
+        e2e_rank_ms = _gather_ranks(1e3 * dt / Ke, dev, world, dist)
         h2d = B * S * S * 3 + B * 48 + B + B * 21 * 8
         d2h = 4 + B * 21 * 8 + B * 21 * 4 + 32 + 32
+        ceil_gbs = _gather_ranks(h2d_ceiling(h2d, dev, world, dist), dev, world, dist)
+        e2e_gbs = h2d * Ke / dt / 1e9
         e2e = {"value": world * B * Ke / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "steps": Ke, "ms_per_step": 1e3 * dt / Ke,
-               "note": "lh_pipeline_submit/wait (C ABI) from pinned host buffers, double-buffered; pred stays device-resident "
-                       "(it is the backbone's output)"}
+               "steps": Ke, "repeats": 3, "ms_per_step": 1e3 * dt / Ke, "h2d_GBps_per_gpu": e2e_gbs,
+               "h2d_ceiling_GBps_per_gpu": ceil_gbs, "frac_of_h2d_ceiling": e2e_gbs / min(ceil_gbs),
+               "note": "lh_pipeline_submit/wait (C ABI) from pinned host buffers, double-buffered, H2D + K1 of step i+1 overlap the "
+                       "loss stage of step i; pred stays device-resident (it is the backbone's output); ceiling = plain pinned "
+                       "cudaMemcpyAsync of the same bytes on all ranks at once"}
         hp.close()
 
     if rank != 0:
         if world > 1:
+            from lighthand_b200.distributed import shutdown
+            shutdown()
             dist.destroy_process_group()
         return 0
 
@@ -420,38 +480,48 @@ def run_ours(args):
     survey_bytes = {True: {256: 2703780, 224: 2070180, 512: 10813860}, False: {256: 2359716, 224: 1806756, 512: 9437604}}[train].get(S)
     step_ms = ms / K
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "repeats": reps,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8->f32 (fixed-point bilinear in int32, heat-maps f32, reductions f64)", "data": "synthetic",
         "config": {"workload": wl["desc"], "global_batch": world * B, "batch_per_gpu": B,
                    "parallelism": f"dp{world} (batch-sharded; one all-reduce of the metric counters per timed region)",
                    "l2": f"inputs larger than L2: ring of {ring} distinct resident batches = {resident_bytes / 1e6:.0f} MB",
                    "materialize_target": bool(args.materialize_target), "train": bool(train),
-                   "launch": "pre-marshalled C-ABI calls, 2 kernels/step (K1; K2+K3+K4+K5 fused)", "normalise": "one FMA per value (<=2 ulp of torch)"},
+                   "launch": "pre-marshalled C-ABI calls, 2 kernels/step (K1 TMA-staged; K2+K3+K4+K5 fused); pipelined: data stage of "
+                             "batch i+1 (K1, data stream) overlaps the loss stage of batch i, as the reference's loader runs ahead of its loop",
+                   "timing": f"median of {reps} repetitions of the K-step region (each bracketed by barrier + synchronize, CUDA events, max over ranks)",
+                   "normalise": "one FMA per value (<=2 ulp of torch)"},
+        "per_rank_ms_per_region": per_rank_ms, "allreduce_us": float(np.median(ar_us)) if world > 1 else 0.0,
+        "serial": {"value": world * B * K / (ms_serial * 1e-3), "unit": UNIT, "ms_per_step": ms_serial / K, "repeats": reps_b,
+                   "note": "the same K steps on ONE stream (K1 then the fused pass, nothing overlapped): the round-1 definition of value"},
         "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
                      "frac_of_nominal_8000GBps": achieved / 8000.0,      # north_star quotes the nominal HBM3e figure too
-                     "traffic": load_traffic("warp_pairs" if dom[0] == "warp_normalize" else "heatmap_vec") if args.workload == "C2" and not args.batch else None,
-                     "traffic_note": "dram__bytes_read+write per launch, ncu --set full (profiles/r01_final_traffic.json); below the algorithmic bytes because part of the output is still dirty in the 126 MB L2 when the kernel ends",
+                     "traffic": load_traffic("warp_tma" if dom[0] == "warp_normalize" else "heatmap_vec") if args.workload == "C2" and not args.batch else None,
+                     "traffic_note": "dram__bytes_read+write per launch, ncu --set full (profiles/r02_traffic.json); below the algorithmic bytes because part of the output is still dirty in the 126 MB L2 when the kernel ends",
                      "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": dom[1], "avg_launch_ms": dom[2]},
+                     "algorithmic_bytes_per_launch": dom[1], "avg_launch_ms": dom[2],
+                     "timed": "serial region B (CUDA events between the two launches on the launching stream)"},
         "kernels": {"warp_normalize": {"ms": k1_ms, "GBps": k1_bytes / (k1_ms * 1e-3) / 1e9, "bytes": k1_bytes},
                     "heatmap_fused": {"ms": fused_ms, "GBps": fused_bytes / (fused_ms * 1e-3) / 1e9, "bytes": fused_bytes},
-                    "rest_ms": step_ms - k1_ms - fused_ms},
+                    "rest_ms": ms_serial / K - k1_ms - fused_ms},
         "pipeline_roofline": {"moved_bytes_per_image": ab["step"], "moved_GBps": ab["step"] * B / (step_ms * 1e-3) / 1e9,
                               "moved_frac_of_peak": ab["step"] * B / (step_ms * 1e-3) / 1e9 / peak,
                               "survey_unfused_bytes_per_image": survey_bytes,
                               "survey_equiv_GBps": (survey_bytes * B / (step_ms * 1e-3) / 1e9) if survey_bytes else None},
-        "two_stream": overlap,
         "cpu_baseline": cpu,
         "e2e": e2e,
         "host_affinity_cores": numa,
         "gpu_launches": pipe.launches_per_step * K,
         "clocks": clocks,
-        "check": {"pck@0.2": metrics["pck"], "epe_px": metrics["epe"], "loss": metrics["loss"], "n_images": metrics["n_images"]},
+        "check": {"all_reduced_over_ranks": world, "pck@0.2": metrics["pck"], "epe_px": metrics["epe"], "loss": metrics["loss"],
+                  "n_images": metrics["n_images"], "n_wrong": metrics["n_wrong"], "n_total": metrics["n_total"],
+                  "overlapped_n_wrong": metrics_ov["n_wrong"], "overlapped_n_images": metrics_ov["n_images"]},
     }
     print(json.dumps(line), flush=True)
     if world > 1:
+        from lighthand_b200.distributed import shutdown
+        shutdown()
         dist.destroy_process_group()
     return 0
 
@@ -459,7 +529,11 @@ def run_ours(args):
 def run_eval_sweep(args):
     """BASELINE.json configs[3]: the full 99,792-image evaluation, batch-sharded across the ranks (strong
     scaling).  Per batch: K1 warp+normalise, fused targets/loss/decode/PCK@0.2/EPE, PCK-curve histogram update;
-    at the end ONE all-reduce of the packed counters and the curve state, then AUC / EPE on the host."""
+    at the end ONE all-reduce of the packed counters and the curve state, then AUC / EPE on the host.
+
+    The data set is ONE sequence of 99,792 samples indexed globally (sample g = pool[g mod P], P = ring x batch distinct
+    synthetic samples); rank r evaluates the contiguous slice shard_range(total, r, world) of it, so the all-reduced
+    counters of an N-rank run must equal the 1-rank run's bit for bit (integers) / to 1e-12 (float64 sums)."""
     wl = WORKLOADS["C4"]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -467,69 +541,83 @@ def run_eval_sweep(args):
     import torch
     import torch.distributed as dist
     from lighthand_b200 import ops
-    from lighthand_b200.distributed import all_reduce_metrics, shard_range
+    from lighthand_b200.distributed import shard_range
     from lighthand_b200.pipeline import HeatmapPipeline
     from lighthand_b200.utils.argparser import CurveAccumulator
     from lighthand_b200.utils.preprocessing import batch_patch_matrices
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    numa = bind_to_gpu_cpus(local) if world > 1 else None     # pinned e2e buffers land next to this rank's GPU
+    comm = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        from lighthand_b200.distributed import metric_comm
+        comm = metric_comm()
     B, S, H, sigma, total = wl["batch"], wl["S"], wl["H"], wl["sigma"], wl["total"]
+    if args.total:
+        total = args.total
     lo, hi = shard_range(total, rank, world)
     n_local = hi - lo
     full, tail = divmod(n_local, B)
     ring = max(2, args.ring)
+    P = ring * B
     stride = S / H
-    g = torch.Generator(device=dev).manual_seed(4321 + rank)
 
-    def make_sets(pipe, nb, count):
-        out = []
-        for r_i in range(count):
-            imgs, joints, bbox, scale, rot, flip = synth_host(nb, S, seed=(4321 + rank) * 100 + r_i)
-            trans, _ = batch_patch_matrices(bbox, flip, scale, rot, (S, S), (S, S))
-            vis = (np.random.default_rng(r_i).uniform(size=(nb, 21, 1)) < 0.8).astype(np.float32)
-            d_j = torch.from_numpy(np.concatenate([joints, vis], -1)).to(dev)
-            tgt, _ = ops.gen_targets(d_j, (H, H), (stride, stride), sigma, want_weight=False)
-            d_pred = tgt + 0.1 * torch.randn(tgt.shape, device=dev, generator=g)
-            cat = torch.randint(0, 4, (nb,), device=dev, dtype=torch.int32, generator=g)
-            step = pipe.prepare(torch.from_numpy(imgs).to(dev), torch.from_numpy(np.ascontiguousarray(trans.astype(np.float64))).to(dev),
-                                d_j, d_pred, flip=torch.from_numpy(np.ascontiguousarray(flip.astype(np.uint8))).to(dev))
-            out.append((step, d_j, cat))
-        return out
+    # the pool, stored twice back to back so that any B consecutive global indices are one contiguous slice
+    parts = [synth_host(B, S, seed=432100 + r_i) for r_i in range(ring)]
+    imgs = np.concatenate([p[0] for p in parts]); joints = np.concatenate([p[1] for p in parts])
+    bbox = np.concatenate([p[2] for p in parts]); scale = np.concatenate([p[3] for p in parts])
+    rot = np.concatenate([p[4] for p in parts]); flip = np.concatenate([p[5] for p in parts])
+    trans, _ = batch_patch_matrices(bbox, flip, scale, rot, (S, S), (S, S))
+    vis = (np.random.default_rng(7).uniform(size=(P, 21, 1)) < 0.8).astype(np.float32)
+    cat = np.random.default_rng(8).integers(0, 4, P).astype(np.int32)
+    twice = lambda a: torch.from_numpy(np.ascontiguousarray(np.concatenate([a, a]))).to(dev)
+    d_imgs, d_M, d_fl = twice(imgs), twice(trans.astype(np.float64)), twice(flip.astype(np.uint8))
+    d_j, d_cat = twice(np.concatenate([joints, vis], -1)), twice(cat)
+    tgt, _ = ops.gen_targets(d_j[:P], (H, H), (stride, stride), sigma, want_weight=False)
+    g = torch.Generator(device=dev).manual_seed(77)
+    pred1 = tgt + 0.1 * torch.randn(tgt.shape, device=dev, generator=g)
+    d_pred = torch.cat([pred1, pred1])
+    del tgt, pred1
 
     pipe = HeatmapPipeline(B, (S, S), (S, S), (H, H), sigma=sigma, train=False, device=dev)
-    sets = make_sets(pipe, B, ring)
     pipe_t = HeatmapPipeline(tail, (S, S), (S, S), (H, H), sigma=sigma, train=False, device=dev) if tail else None
-    sets_t = make_sets(pipe_t, tail, 1) if tail else []
     acc = CurveAccumulator([0, 30], "mm", device=dev)
+    prepared = {}
+
+    def batch(pp, start, nb):
+        """pre-marshalled step + joints + categories of the nb samples at global index `start`"""
+        o = start % P
+        key = (id(pp), o, nb)
+        if key not in prepared:
+            sl = slice(o, o + nb)
+            prepared[key] = (pp.prepare(d_imgs[sl], d_M[sl], d_j[sl], d_pred[sl], flip=d_fl[sl]), d_j[sl], d_cat[sl])
+        return prepared[key]
 
     def sweep():
         for i in range(full):
-            step, d_j, cat = sets[i % ring]
+            step, jj, cc = batch(pipe, lo + i * B, B)
             step.launch()
-            acc.update(pipe.buffers["coords"], d_j, None, cat)
+            acc.update(pipe.buffers["coords"], jj, None, cc)
         if tail:
-            step, d_j, cat = sets_t[0]
+            step, jj, cc = batch(pipe_t, lo + full * B, tail)
             step.launch()
-            acc.update(pipe_t.buffers["coords"], d_j, None, cat)
+            acc.update(pipe_t.buffers["coords"], jj, None, cc)
             # fold the tail pipeline's counters into the main accumulators
             pipe.meter.counts.add_(pipe_t.meter.counts); pipe.meter.sums.add_(pipe_t.meter.sums)
             pipe_t.reset_metrics()
-        if world > 1:
-            all_reduce_metrics([pipe.meter.counts, pipe.meter.sums] + acc.tensors())
+        if comm is not None:
+            comm.all_reduce([pipe.meter.counts, pipe.meter.sums] + acc.tensors())
 
     def reset():
         pipe.reset_metrics()
         for t in acc.tensors():
             t.zero_()
 
-    for _ in range(max(1, min(args.warmup, 2))):
+    for _ in range(2):
         sweep()
     torch.cuda.synchronize()
-    reps = max(1, min(args.steps, 5))
+    reps = max(3, min(args.steps, 7))
     times = []
     for _ in range(reps):
         reset()
@@ -541,29 +629,31 @@ def run_eval_sweep(args):
         sweep()
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        times.append(ms)
+        times.append(_max_over_ranks(e0.elapsed_time(e1), dev, world, dist))
     res = acc.finalize()
     m = pipe.meter.result()
+    hist = acc.hist.sum(0).cpu().numpy().astype(np.uint64)
     if rank == 0:
+        import hashlib
         ms = float(np.median(times))
         line = {
             "metric": METRIC, "value": total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": reps, "warmup": 2,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u8->f32", "data": "synthetic (ring of %d resident batches per rank, reused across the sweep)" % ring,
+            "dtype": "u8->f32", "data": "synthetic: one globally indexed data set (sample g = pool[g mod %d]), each rank evaluates its shard_range slice" % P,
             "config": {"workload": wl["desc"], "global_batch": total, "batch_per_gpu": B, "images_per_rank": n_local,
-                       "parallelism": f"dp{world} (contiguous shards, one all-reduce of counters + curve histograms)"},
-            "check": {"n_images": m["n_images"], "n_wrong": m["n_wrong"], "n_total": m["n_total"], "pck@0.2": m["pck"],
-                      "epe_px": m["epe"], "mean_auc": float(res["mean_auc"][0]), "mean_epe_mm": float(res["mean_auc"][1]),
-                      "curve_count_at_T50": int(acc.hist.sum(0)[:50].sum().item())},
+                       "parallelism": f"dp{world} (contiguous shards, one grouped NCCL all-reduce of counters + curve histograms)"},
+            "check": {"all_reduced_over_ranks": world, "n_images": m["n_images"], "n_wrong": m["n_wrong"], "n_total": m["n_total"],
+                      "epe_count": m["epe_count"], "pck@0.2": m["pck"],
+                      "epe_px": m["epe"], "epe_sum": m["epe_sum"], "loss": m["loss"], "mean_auc": float(res["mean_auc"][0]),
+                      "mean_epe_mm": float(res["mean_auc"][1]),
+                      "curve_count_at_T50": int(hist[:50].sum()), "curve_hist_sha1": hashlib.sha1(hist.tobytes()).hexdigest(),
+                      "curve_n_valid": int(acc.n_valid.sum().item())},
             "gpu_launches": 3 * (full + (1 if tail else 0)),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        from lighthand_b200.distributed import shutdown
+        shutdown()
         dist.destroy_process_group()
     return 0
 
@@ -571,15 +661,15 @@ def run_eval_sweep(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5000)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--ring", type=int, default=4)
     ap.add_argument("--materialize-target", action="store_true")
-    ap.add_argument("--no-overlap", dest="overlap", action="store_false",
-                    help="skip the extra timing of the step with K1 and the fused pass on two streams")
+    ap.add_argument("--repeats", type=int, default=0, help="repetitions of the K-step timed region (0: enough for ~250 ms)")
+    ap.add_argument("--total", type=int, default=0, help="C4: evaluate this many samples instead of 99,792")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=70)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define LH_ABI_VERSION 3
+#define LH_ABI_VERSION 4
 
 #define LH_OK            0
 #define LH_EINVAL       (-1)  /* bad size / enum value */
@@ -35,6 +35,7 @@ extern "C" {
 #define LH_EUNSUPPORTED (-4)  /* geometry outside what the kernels implement */
 #define LH_ENOMEM       (-5)  /* workspace too small / allocation failed (pipeline ctx) */
 #define LH_ENODEVICE    (-6)  /* no sm_100 device */
+#define LH_ENCCL        (-7)  /* NCCL missing (libnccl.so.2 could not be loaded) or an NCCL call failed */
 
 typedef void* lh_stream_t; /* cudaStream_t */
 
@@ -192,6 +193,31 @@ int lh_pck_curve_accum(const float* pred_xy, const float* gt, int gt_stride,
                        unsigned long long* n_all, double* sum_d, lh_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K6  metric all-reduce: the path's only collective.  The batch is data-partitioned, one
+ * process per GPU; ranks exchange nothing but the SUM of the additive accumulators above -- the state of the
+ * reference's AverageMeters (src/utils/metric_logger.py:7-28, src/utils/method.py:241-250) and of pred_eval's
+ * counting loops (src/utils/argparser.py:347-378); src/utils/comm.py (never initialised in the reference) is the
+ * role it takes.  NCCL over NVLink 5 / NVSwitch, in place, stream-ordered (enqueue it right after the last K5 on
+ * the same stream: no host synchronisation), CUDA-graph capturable.  Integer counts are order-independent:
+ * N ranks give the 1-rank result bit for bit; float64 sums differ by reduction order only.
+ *   lh_comm_unique_id   rank 0 makes the 128-byte id and ships it to the other ranks by any means (MPI, sockets,
+ *                       the torch.distributed store: lighthand_b200/distributed.py)
+ *   lh_comm_init        collective over all ranks (ncclCommInitRank on `device`)
+ *   lh_metrics_allreduce        counts u64[n_counts] and sums f64[n_sums] as ONE grouped NCCL operation
+ *   lh_metrics_allreduce_multi  the same for any number of u64 / f64 buffers (curve histograms of an evaluation
+ *                               sweep next to the loop counters): one grouped operation, no packing copies
+ * NCCL is bound at run time; without libnccl.so.2 these four return LH_ENCCL and everything else works.
+ * ------------------------------------------------------------------------------------------ */
+#define LH_COMM_ID_BYTES 128
+int lh_comm_unique_id(void* id_out /* host, LH_COMM_ID_BYTES */);
+int lh_comm_init(const void* id, int world, int rank, int device, void** comm_out);
+int lh_comm_destroy(void* comm);
+int lh_metrics_allreduce(void* comm, unsigned long long* counts, int n_counts, double* sums, int n_sums,
+                         lh_stream_t stream);
+int lh_metrics_allreduce_multi(void* comm, int n_bufs, void* const* bufs /* dev */, const size_t* elems,
+                               const int* is_f64 /* 0: uint64, 1: float64 */, lh_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * FreiHAND image path.  Replaces, batched:
  *   crop / myimrotate / myimresize        src/utils/image_ops.py:25-56, 97-131
  *   HandMeshTSVDataset.rgb_processing     src/datasets/frei_dataloader.py:134-147   (flip is always 0, :107)
@@ -253,8 +279,11 @@ int lh_color_jitter_normalize(const float* src, const lh_jitter_params* params, 
 
 /* ------------------------------------------------------------------------------------------
  * Host-buffer pipeline context (what a non-torch host binds; also the e2e benchmark path).
- * Owns device buffers, pinned staging and two streams; one step is
- *   H2D -> K1 -> fused(K2,K3,K4,K5) -> D2H   (two kernel launches).
+ * Owns device buffers, pinned staging and three streams; one step is
+ *   data stage   H2D -> K1 -> input[slot]                       (copy + data streams)
+ *   loss stage   [backbone] -> fused(K2,K3,K4,K5) -> D2H        (loss stream)
+ * two kernel launches; the data stage of step i+1 overlaps the loss stage of step i, as the data loader of the
+ * reference's loop runs ahead of the model (src/utils/method.py:160-183).
  * ------------------------------------------------------------------------------------------ */
 typedef struct lh_pipeline_cfg {
     int32_t device;
@@ -291,7 +320,8 @@ typedef struct lh_pipeline_io {
 int lh_pipeline_create(const lh_pipeline_cfg* cfg, const float* gauss_table_host, int table_side, lh_pipeline** out);
 void lh_pipeline_destroy(lh_pipeline* p);
 /* device-resident buffers of the context (backbone input / output live here) */
-float* lh_pipeline_input_dev(lh_pipeline* p);   /* [N,3,out_h,out_w] normalised images  */
+float* lh_pipeline_input_dev(lh_pipeline* p);            /* [N,3,out_h,out_w] normalised images of the LAST submitted slot */
+float* lh_pipeline_input_dev_slot(lh_pipeline* p, int slot);   /* each of the two slots owns its input buffer        */
 float* lh_pipeline_pred_dev(lh_pipeline* p);    /* [N,J,H,W] where the backbone writes   */
 float* lh_pipeline_grad_dev(lh_pipeline* p);    /* [N,J,H,W] d loss / d pred             */
 float* lh_pipeline_target_dev(lh_pipeline* p);  /* [N,J,H,W] or NULL                     */
@@ -299,9 +329,22 @@ float* lh_pipeline_target_dev(lh_pipeline* p);  /* [N,J,H,W] or NULL            
  * outputs are valid (synchronous w.r.t. the host). */
 int lh_pipeline_step_host(lh_pipeline* p, const lh_pipeline_io* io);
 /* asynchronous pair (two slots, double-buffered): submit step i+1 before waiting for step i so its
- * host->device copy overlaps step i's kernels.  The io pointers must stay valid until the wait. */
+ * host->device copy and its K1 overlap step i's loss stage.  The io pointers must stay valid until the wait. */
 int lh_pipeline_submit(lh_pipeline* p, const lh_pipeline_io* io, int* slot_out);
 int lh_pipeline_wait(lh_pipeline* p, int slot);
+/* the two halves of lh_pipeline_submit, for a host that runs the backbone between them:
+ *   lh_pipeline_submit_inputs(p, io, &slot);                 data stage; the loss stream now waits for K1
+ *   <enqueue the backbone on lh_pipeline_loss_stream(p): reads lh_pipeline_input_dev_slot(p, slot),
+ *    writes lh_pipeline_pred_dev(p)>
+ *   lh_pipeline_submit_loss(p, slot);                        loss stage + result copies
+ *   lh_pipeline_wait(p, slot); */
+int lh_pipeline_submit_inputs(lh_pipeline* p, const lh_pipeline_io* io, int* slot_out);
+int lh_pipeline_submit_loss(lh_pipeline* p, int slot);
+void* lh_pipeline_loss_stream(lh_pipeline* p);   /* cudaStream_t */
+/* multi-GPU: SUM the running accumulators over `comm` (lh_comm_init), ordered after the last submitted loss stage;
+ * lh_pipeline_read_metrics = synchronous read of counts u64[4] / sums f64[4] (see lh_pipeline_io) */
+int lh_pipeline_allreduce_metrics(lh_pipeline* p, void* comm);
+int lh_pipeline_read_metrics(lh_pipeline* p, unsigned long long* counts4, double* sums4);
 int lh_pipeline_reset_metrics(lh_pipeline* p);
 /* number of kernel launches one step issues (for accounting) */
 int lh_pipeline_launches_per_step(const lh_pipeline* p);

@@ -17,6 +17,8 @@ LH_CHAN_RGB, LH_CHAN_BGR = 0, 1
 LH_LAYOUT_CHW, LH_LAYOUT_HWC = 0, 1
 LH_TARGET_HRNET, LH_TARGET_HOURGLASS = 0, 1
 LH_PCK_PROPORTION, LH_PCK_MM = 0, 1
+LH_COMM_ID_BYTES = 128
+ABI_VERSION = 4
 
 c_p = C.c_void_p
 c_i = C.c_int
@@ -99,10 +101,21 @@ PROTOTYPES = {
     "lh_pipeline_step_host": (c_i, [c_p, C.POINTER(PipelineIO)]),
     "lh_pipeline_submit": (c_i, [c_p, C.POINTER(PipelineIO), C.POINTER(c_i)]),
     "lh_pipeline_wait": (c_i, [c_p, c_i]),
+    "lh_pipeline_submit_inputs": (c_i, [c_p, C.POINTER(PipelineIO), C.POINTER(c_i)]),
+    "lh_pipeline_submit_loss": (c_i, [c_p, c_i]),
+    "lh_pipeline_loss_stream": (c_p, [c_p]),
+    "lh_pipeline_input_dev_slot": (c_p, [c_p, c_i]),
+    "lh_pipeline_allreduce_metrics": (c_i, [c_p, c_p]),
+    "lh_pipeline_read_metrics": (c_i, [c_p, c_p, c_p]),
     "lh_pipeline_reset_metrics": (c_i, [c_p]),
     "lh_pipeline_launches_per_step": (c_i, [c_p]),
     "lh_host_alloc": (c_p, [C.c_size_t]),
     "lh_host_free": (None, [c_p]),
+    "lh_comm_unique_id": (c_i, [c_p]),
+    "lh_comm_init": (c_i, [c_p, c_i, c_i, c_i, C.POINTER(c_p)]),
+    "lh_comm_destroy": (c_i, [c_p]),
+    "lh_metrics_allreduce": (c_i, [c_p, c_p, c_i, c_p, c_i, c_p]),
+    "lh_metrics_allreduce_multi": (c_i, [c_p, c_i, C.POINTER(c_p), C.POINTER(C.c_size_t), C.POINTER(c_i), c_p]),
 }
 
 _lib = None
@@ -122,7 +135,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so is stale
         fn.restype = res
         fn.argtypes = args
-    if lib.lh_abi_version() != 3:
+    if lib.lh_abi_version() != ABI_VERSION:
         raise LighthandError("liblighthand_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

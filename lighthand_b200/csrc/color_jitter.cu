@@ -109,11 +109,13 @@ __global__ void __launch_bounds__(kJitThreads) jitter_mean_kernel(const float* _
     }
 }
 
-__global__ void __launch_bounds__(kJitThreads) jitter_apply_kernel(const float* __restrict__ src,
+// src and dst may be the same buffer (include/lighthand_b200.h): no __restrict__ / non-coherent loads on them; a thread
+// reads its three channel values before it writes them, and no other thread touches those elements.
+__global__ void __launch_bounds__(kJitThreads) jitter_apply_kernel(const float* src,
                                                                    const lh_jitter_params* __restrict__ params, int hw,
                                                                    const double* __restrict__ ws, int normalise, float m0,
                                                                    float m1, float m2, float s0, float s1, float s2,
-                                                                   float* __restrict__ dst) {
+                                                                   float* dst) {
     const int n = blockIdx.y;
     const lh_jitter_params jp = params[n];
     float mean = 0.0f;
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(kJitThreads) jitter_apply_kernel(const float* 
     const float* pr = src + (size_t)n * 3 * hw;
     float* po = dst + (size_t)n * 3 * hw;
     for (int i = blockIdx.x * kJitThreads + threadIdx.x; i < hw; i += gridDim.x * kJitThreads) {
-        float r = __ldg(pr + i), g = __ldg(pr + hw + i), b = __ldg(pr + 2 * (size_t)hw + i);
+        float r = pr[i], g = pr[hw + i], b = pr[2 * (size_t)hw + i];
         if (jp.apply) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) apply_fn(jp.order[k], jp, mean, r, g, b);

@@ -262,7 +262,7 @@ __device__ __forceinline__ void final_reduce(const HeatmapParams& p, bool do_met
 //   A  after the streaming pass: per-warp loss partial + NaN-propagating maximum
 //   B  after the winner search: smallest index holding the maximum (numpy's first-index tie-break)
 // Warp 0 then finishes the map (coordinates, outputs, metric record) while the other warps are already
-// streaming the next one; reduction scratch is double-buffered by iteration parity.
+// streaming the next one; reduction scratch is triple-buffered by map count (see s_sum below).
 // ------------------------------------------------------------------------------------------------
 constexpr int F_GRAD = 1, F_TOUT = 2, F_DEC = 4, F_WGT = 8;
 
@@ -314,9 +314,11 @@ __global__ void __launch_bounds__(kVecThreads, TSRC == 2 ? 4 : 8) heatmap_vec_ke
     using Body = VecBody<PRED, TSRC, FLAGS>;
     constexpr bool GRAD = Body::GRAD, TOUT = Body::TOUT, DEC = Body::DEC, WGT = Body::WGT, LOSS = Body::LOSS;
     __shared__ float s_tab[TSRC == 1 ? kMaxTable : 1];
-    __shared__ double s_sum[2][kVecThreads / kWarp];
-    __shared__ __align__(16) float s_max[2][kVecThreads / kWarp];
-    __shared__ __align__(16) int s_idx[2][kVecThreads / kWarp];
+    // reduction scratch, TRIPLE-buffered by map count: after barrier A of map i warp 0 still reads map i-1's slots
+    // ("finish the previous map one barrier late") while the other warps already write map i+1's
+    __shared__ double s_sum[3][kVecThreads / kWarp];
+    __shared__ __align__(16) float s_max[3][kVecThreads / kWarp];
+    __shared__ __align__(16) int s_idx[3][kVecThreads / kWarp];
     static_assert(kVecThreads / kWarp == 4, "the float4 / int4 reads of s_max / s_idx assume 4 warps");
     __shared__ double s_fin[kVecThreads / kWarp];
     __shared__ unsigned int s_finc[kVecThreads / kWarp];
@@ -458,14 +460,15 @@ __global__ void __launch_bounds__(kVecThreads, TSRC == 2 ? 4 : 8) heatmap_vec_ke
             if (lane == 0) { if (LOSS) s_sum[par][warp] = (double)wsum; if (DEC) s_max[par][warp] = wmax; }
             __syncthreads();
             // the barrier also published the previous map's winner indices: warp 0 finishes that map now
-            if (warp == 0 && pm >= 0) LH_FINISH_PREV(pm, par ^ 1)
+            if (warp == 0 && pm >= 0) LH_FINISH_PREV(pm, (par + 2) % 3)
             if (DEC) {
                 const float4 ma = *reinterpret_cast<const float4*>(&s_max[par][0]);
                 const float M = max_nan(max_nan(ma.x, ma.y), max_nan(ma.z, ma.w));
                 const bool mnan = M != M;
                 int cand = 0x7fffffff;
                 // threads whose own maximum IS the map maximum look up its first position inside their vector
-                if (active && (mnan ? (tmax != tmax) : (tmax == M))) {
+                // (threads that own no row of a map with H < rows-per-pass keep tvec outside the map: r0 < H)
+                if (active && r0 < H && (mnan ? (tmax != tmax) : (tmax == M))) {
                     const float4 q = *reinterpret_cast<const float4*>(p.pred + (size_t)m * p.HW + tvec);
                     const float v[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
@@ -475,14 +478,14 @@ __global__ void __launch_bounds__(kVecThreads, TSRC == 2 ? 4 : 8) heatmap_vec_ke
                 if (lane == 0) s_idx[par][warp] = cand;
             }
             pm = m;
-            par ^= 1;
+            par = (par + 1) % 3;
         }
         m = m2; g = g2;
     }
 
     if (!PRED) return;
     __syncthreads();                                  // publishes the last map's winner indices
-    if (warp == 0 && pm >= 0) LH_FINISH_PREV(pm, par ^ 1)
+    if (warp == 0 && pm >= 0) LH_FINISH_PREV(pm, (par + 2) % 3)
 #undef LH_ISSUE
 #undef LH_FINISH_PREV
     if ((LOSS && (p.loss_f64 || p.loss_f32 || p.loss_meter)) || do_metric) {

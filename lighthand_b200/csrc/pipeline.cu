@@ -1,10 +1,15 @@
 // Host-buffer pipeline context: what a host without torch binds, and the end-to-end path
 // (host u8 images + matrices + joints in, loss / coordinates / metric counts out).
 //
-// Two slots are double-buffered so the H2D copy of step i+1 (copy stream, DMA engine) overlaps
-// the kernels of step i (compute stream); ordering is by CUDA events only, the host blocks once
-// per step on the slot's "done" event.  Kernels per step: K1 warp+normalise, fused K2+K3+K4+K5
-// (2 launches; the normalisation table is built once at create time).
+// Two slots, three streams, ordering by CUDA events only (the host blocks once per step on the slot's "done"
+// event):
+//   copy stream   H2D of step i+1 (DMA engine)                    } overlap the
+//   data stream   K1 warp+normalise of step i+1 -> input[slot]    } loss stage of step i
+//   loss stream   [the caller's backbone] -> fused K2+K3+K4+K5 of step i -> D2H of the results
+// which is the shape of the reference's loop (src/utils/method.py:160-183): the data stage of the next batch runs
+// ahead of the model / loss stage of the current one.  K1 and the fused pass touch disjoint buffers, so they may
+// run concurrently; each slot owns its network-input buffer.  Kernels per step: 2 launches (the normalisation
+// table is built once at create time).
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -23,10 +28,12 @@ struct Slot {
     float* d_coords = nullptr;
     float* d_maxvals = nullptr;
     float* d_loss = nullptr;
+    float* d_input = nullptr;   // this slot's network input [N,3,out_h,out_w] (K1 of the next step must not overwrite it)
     // pinned result block: loss[1] | coords[N*J*2] | maxvals[N*J] | counts u64[4] | sums f64[4]
     unsigned char* h_out = nullptr;
-    cudaEvent_t ev_h2d = nullptr, ev_done = nullptr;
-    bool busy = false;
+    cudaEvent_t ev_h2d = nullptr, ev_k1 = nullptr, ev_done = nullptr;
+    bool busy = false;        // submitted (inputs at least), not yet waited
+    bool loss_pending = false; // lh_pipeline_submit_inputs done, lh_pipeline_submit_loss not yet
     lh_pipeline_io io{};
 };
 
@@ -35,9 +42,9 @@ struct Slot {
 struct lh_pipeline {
     lh_pipeline_cfg cfg{};
     int table_side = 0;
-    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaStream_t s_copy = nullptr, s_data = nullptr, s_comp = nullptr;   // s_comp = the loss stream
     Slot slot[kSlots];
-    float* d_input = nullptr;
+    int last_slot = 0;
     float* d_pred = nullptr;
     float* d_target = nullptr;
     float* d_grad = nullptr;
@@ -60,17 +67,20 @@ extern "C" void lh_pipeline_destroy(lh_pipeline* p) {
     if (!p) return;
     cudaSetDevice(p->cfg.device);
     if (p->s_comp) cudaStreamSynchronize(p->s_comp);
+    if (p->s_data) cudaStreamSynchronize(p->s_data);
     if (p->s_copy) cudaStreamSynchronize(p->s_copy);
     for (auto& s : p->slot) {
         cudaFree(s.d_images); cudaFree(s.d_affine); cudaFree(s.d_flip); cudaFree(s.d_joints);
-        cudaFree(s.d_coords); cudaFree(s.d_maxvals); cudaFree(s.d_loss);
+        cudaFree(s.d_coords); cudaFree(s.d_maxvals); cudaFree(s.d_loss); cudaFree(s.d_input);
         if (s.h_out) cudaFreeHost(s.h_out);
         if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+        if (s.ev_k1) cudaEventDestroy(s.ev_k1);
         if (s.ev_done) cudaEventDestroy(s.ev_done);
     }
-    cudaFree(p->d_input); cudaFree(p->d_pred); cudaFree(p->d_target); cudaFree(p->d_grad);
+    cudaFree(p->d_pred); cudaFree(p->d_target); cudaFree(p->d_grad);
     cudaFree(p->d_table); cudaFree(p->d_lut); cudaFree(p->d_ws); cudaFree(p->d_counts); cudaFree(p->d_sums);
     if (p->s_copy) cudaStreamDestroy(p->s_copy);
+    if (p->s_data) cudaStreamDestroy(p->s_data);
     if (p->s_comp) cudaStreamDestroy(p->s_comp);
     delete p;
 }
@@ -91,6 +101,7 @@ extern "C" int lh_pipeline_create(const lh_pipeline_cfg* cfg, const float* table
     const size_t img_bytes = (size_t)cfg->src_h * cfg->src_w * 3;
     PCHK(cudaSetDevice(cfg->device));
     PCHK(cudaStreamCreateWithFlags(&p->s_copy, cudaStreamNonBlocking));
+    PCHK(cudaStreamCreateWithFlags(&p->s_data, cudaStreamNonBlocking));
     PCHK(cudaStreamCreateWithFlags(&p->s_comp, cudaStreamNonBlocking));
     p->off_coords = 16;
     p->off_maxvals = p->off_coords + N * J * 2 * sizeof(float);
@@ -106,11 +117,12 @@ extern "C" int lh_pipeline_create(const lh_pipeline_cfg* cfg, const float* table
         PCHK(cudaMalloc(&s.d_coords, N * J * 2 * sizeof(float)));
         PCHK(cudaMalloc(&s.d_maxvals, N * J * sizeof(float)));
         PCHK(cudaMalloc(&s.d_loss, 16));
+        PCHK(cudaMalloc(&s.d_input, N * 3 * (size_t)cfg->out_h * cfg->out_w * sizeof(float)));
         PCHK(cudaMallocHost(&s.h_out, p->out_bytes));
         PCHK(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+        PCHK(cudaEventCreateWithFlags(&s.ev_k1, cudaEventDisableTiming));
         PCHK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
     }
-    PCHK(cudaMalloc(&p->d_input, N * 3 * (size_t)cfg->out_h * cfg->out_w * sizeof(float)));
     PCHK(cudaMalloc(&p->d_pred, N * J * HW * sizeof(float)));
     PCHK(cudaMemset(p->d_pred, 0, N * J * HW * sizeof(float)));
     if (cfg->materialize_target) PCHK(cudaMalloc(&p->d_target, N * J * HW * sizeof(float)));
@@ -137,7 +149,11 @@ fail:
     return rc;
 }
 
-extern "C" float* lh_pipeline_input_dev(lh_pipeline* p) { return p ? p->d_input : nullptr; }
+extern "C" float* lh_pipeline_input_dev(lh_pipeline* p) { return p ? p->slot[p->last_slot].d_input : nullptr; }
+extern "C" float* lh_pipeline_input_dev_slot(lh_pipeline* p, int slot) {
+    return (p && slot >= 0 && slot < kSlots) ? p->slot[slot].d_input : nullptr;
+}
+extern "C" void* lh_pipeline_loss_stream(lh_pipeline* p) { return p ? (void*)p->s_comp : nullptr; }
 extern "C" float* lh_pipeline_pred_dev(lh_pipeline* p) { return p ? p->d_pred : nullptr; }
 extern "C" float* lh_pipeline_grad_dev(lh_pipeline* p) { return p ? p->d_grad : nullptr; }
 extern "C" float* lh_pipeline_target_dev(lh_pipeline* p) { return p ? p->d_target : nullptr; }
@@ -152,15 +168,16 @@ extern "C" int lh_pipeline_reset_metrics(lh_pipeline* p) {
     return (int)e;
 }
 
-// enqueue one step into slot (step % 2) and report the slot through *slot_out
-extern "C" int lh_pipeline_submit(lh_pipeline* p, const lh_pipeline_io* io, int* slot_out) {
+// data stage of one step into slot (step % 2): H2D on the copy stream, K1 on the data stream; the loss stream is
+// made to wait for K1, so whatever the caller enqueues on lh_pipeline_loss_stream() next (the backbone) sees the input
+extern "C" int lh_pipeline_submit_inputs(lh_pipeline* p, const lh_pipeline_io* io, int* slot_out) {
     if (!p || !io || !io->images || !io->joints || !slot_out) return LH_ENULL;
     const lh_pipeline_cfg& c = p->cfg;
     if (c.interp != LH_INTERP_TORCH && !io->fwd_affine) return LH_ENULL;
     const int si = (int)(p->step % kSlots);
     Slot& s = p->slot[si];
     if (s.busy) return LH_EINVAL;  // caller must lh_pipeline_wait() the slot first
-    const size_t N = c.batch, J = c.J, HW = (size_t)c.H * c.W;
+    const size_t N = c.batch, J = c.J;
     const size_t img_bytes = (size_t)c.src_h * c.src_w * 3;
     int rc = LH_OK;
     PCHK(cudaSetDevice(c.device));
@@ -169,19 +186,39 @@ extern "C" int lh_pipeline_submit(lh_pipeline* p, const lh_pipeline_io* io, int*
     if (io->fwd_affine) PCHK(cudaMemcpyAsync(s.d_affine, io->fwd_affine, N * 6 * sizeof(double), cudaMemcpyHostToDevice, p->s_copy));
     if (io->flip) PCHK(cudaMemcpyAsync(s.d_flip, io->flip, N, cudaMemcpyHostToDevice, p->s_copy));
     PCHK(cudaMemcpyAsync(s.d_joints, io->joints, N * J * 2 * sizeof(float), cudaMemcpyHostToDevice, p->s_copy));
-    if (io->pred) {
-        // d_pred is shared by both slots: the copy must not overtake the previous step's kernels
-        if (p->step > 0) PCHK(cudaStreamWaitEvent(p->s_copy, p->slot[(si + kSlots - 1) % kSlots].ev_done, 0));
-        PCHK(cudaMemcpyAsync(p->d_pred, io->pred, N * J * HW * sizeof(float), cudaMemcpyHostToDevice, p->s_copy));
-    }
     PCHK(cudaEventRecord(s.ev_h2d, p->s_copy));
-    PCHK(cudaStreamWaitEvent(p->s_comp, s.ev_h2d, 0));
-
+    PCHK(cudaStreamWaitEvent(p->s_data, s.ev_h2d, 0));
     rc = lh_warp_normalize(s.d_images, (int64_t)img_bytes, c.src_h, c.src_w, c.src_w * 3, s.d_affine,
                            io->flip ? s.d_flip : nullptr, nullptr, c.mean_std,
                            (c.exact_norm || c.interp != LH_INTERP_CV2_U8) ? p->d_lut : nullptr, c.interp, LH_CHAN_RGB,
-                           LH_LAYOUT_CHW, p->d_input, (int)N, c.out_h, c.out_w, p->s_comp);
+                           LH_LAYOUT_CHW, s.d_input, (int)N, c.out_h, c.out_w, p->s_data);
     if (rc) goto fail;
+    PCHK(cudaEventRecord(s.ev_k1, p->s_data));
+    PCHK(cudaStreamWaitEvent(p->s_comp, s.ev_k1, 0));
+    s.io = *io;
+    s.busy = true;
+    s.loss_pending = true;
+    p->last_slot = si;
+    p->step++;
+    *slot_out = si;
+    return LH_OK;
+fail:
+    return rc;
+}
+
+// loss stage of the step in `si` on the loss stream: [pred H2D] -> fused K2+K3+K4+K5 -> D2H of the results
+extern "C" int lh_pipeline_submit_loss(lh_pipeline* p, int si) {
+    if (!p) return LH_ENULL;
+    if (si < 0 || si >= kSlots) return LH_EINVAL;
+    Slot& s = p->slot[si];
+    if (!s.busy || !s.loss_pending) return LH_EINVAL;
+    const lh_pipeline_cfg& c = p->cfg;
+    const lh_pipeline_io* io = &s.io;
+    const size_t N = c.batch, J = c.J, HW = (size_t)c.H * c.W;
+    int rc = LH_OK;
+    PCHK(cudaSetDevice(c.device));
+    if (io->pred)   // d_pred is shared by both slots: the loss stream is in order, so this copy follows the previous step's kernels
+        PCHK(cudaMemcpyAsync(p->d_pred, io->pred, N * J * HW * sizeof(float), cudaMemcpyHostToDevice, p->s_comp));
     {
         lh_heatmap_args a{};
         a.pred = p->d_pred; a.joints = s.d_joints; a.gauss_table = p->d_table;
@@ -202,13 +239,36 @@ extern "C" int lh_pipeline_submit(lh_pipeline* p, const lh_pipeline_io* io, int*
     PCHK(cudaMemcpyAsync(s.h_out + p->off_counts, p->d_counts, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->s_comp));
     PCHK(cudaMemcpyAsync(s.h_out + p->off_sums, p->d_sums, 4 * sizeof(double), cudaMemcpyDeviceToHost, p->s_comp));
     PCHK(cudaEventRecord(s.ev_done, p->s_comp));
-    s.io = *io;
-    s.busy = true;
-    p->step++;
-    *slot_out = si;
+    s.loss_pending = false;
     return LH_OK;
 fail:
     return rc;
+}
+
+// one whole step (data stage + loss stage) into slot (step % 2)
+extern "C" int lh_pipeline_submit(lh_pipeline* p, const lh_pipeline_io* io, int* slot_out) {
+    const int rc = lh_pipeline_submit_inputs(p, io, slot_out);
+    if (rc) return rc;
+    return lh_pipeline_submit_loss(p, *slot_out);
+}
+
+// SUM the running metric accumulators over the ranks of `comm` (lh_comm_init), stream-ordered after the last
+// submitted loss stage; every rank calls it the same number of times
+extern "C" int lh_pipeline_allreduce_metrics(lh_pipeline* p, void* comm) {
+    if (!p || !comm) return LH_ENULL;
+    cudaError_t e = cudaSetDevice(p->cfg.device);
+    if (e != cudaSuccess) return (int)e;
+    return lh_metrics_allreduce(comm, p->d_counts, 4, p->d_sums, 4, p->s_comp);
+}
+
+// synchronous read of the running accumulators (after everything submitted so far)
+extern "C" int lh_pipeline_read_metrics(lh_pipeline* p, unsigned long long* counts4, double* sums4) {
+    if (!p || !counts4 || !sums4) return LH_ENULL;
+    cudaError_t e = cudaSetDevice(p->cfg.device);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(counts4, p->d_counts, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->s_comp);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sums4, p->d_sums, 4 * sizeof(double), cudaMemcpyDeviceToHost, p->s_comp);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->s_comp);
+    return (int)e;
 }
 
 // block until slot `si` finished and hand its results to the host pointers given at submit time
@@ -216,7 +276,7 @@ extern "C" int lh_pipeline_wait(lh_pipeline* p, int si) {
     if (!p) return LH_ENULL;
     if (si < 0 || si >= kSlots) return LH_EINVAL;
     Slot& s = p->slot[si];
-    if (!s.busy) return LH_EINVAL;
+    if (!s.busy || s.loss_pending) return LH_EINVAL;   // nothing submitted, or the loss stage is still missing
     cudaSetDevice(p->cfg.device);
     cudaError_t e = cudaEventSynchronize(s.ev_done);
     s.busy = false;

@@ -6,6 +6,10 @@
                      what replaces, per iteration, ``__getitem__``/collate + ``JointsMSELoss`` +
                      ``.cpu()`` + ``get_max_preds`` + ``PCK_2d_loss`` + ``EPE_train`` of the reference's
                      loops (src/utils/method.py:156-287).
+                     ``data_stage`` / ``loss_stage`` (or ``step_overlapped``) run the same two launches as a software
+                     pipeline: K1 of the NEXT batch on an internal data stream while the loss stage of the CURRENT
+                     batch runs on the caller's stream -- the reference's loop shape, where the data loader runs
+                     ahead of model + loss (src/utils/method.py:160-183).  Results are bit-identical to ``step``.
 ``HostPipeline``     the same step through the C-ABI context (lh_pipeline_*): HOST buffers in, host
                      results out, double-buffered so the H2D copy of step i+1 overlaps step i.
 
@@ -43,7 +47,15 @@ class HeatmapPipeline:
         self.stride = (self.out_hw[1] / self.hm_hw[1], self.out_hw[0] / self.hm_hw[0])
         d, f32 = self.device, torch.float32
         n, j, (h, w) = self.N, self.J, self.hm_hw
-        self.input = torch.empty((n, 3, *self.out_hw), dtype=f32, device=d)
+        # network input, one buffer per pipeline slot: ``step`` uses slot 0, the overlapped form alternates so that K1 of
+        # batch i+1 never overwrites what the backbone of batch i is still reading
+        self.inputs = [torch.empty((n, 3, *self.out_hw), dtype=f32, device=d) for _ in range(2)]
+        self.input = self.inputs[0]
+        self._dstream = None            # data stream + events of the overlapped form (created on first use)
+        self._ev_k1 = self._ev_free = None
+        self._free_valid = [False, False]
+        self._next_slot = 0
+        self._pending = []
         self.buffers = {
             "loss": torch.zeros((), dtype=f32, device=d),
             "coords": torch.empty((n, j, 2), dtype=f32, device=d),
@@ -107,6 +119,85 @@ class HeatmapPipeline:
         out.pop("ws")
         return out
 
+    # -- the same step as a two-stage software pipeline ---------------------------------------------
+    def _overlap_state(self):
+        if self._dstream is None:
+            self._dstream = torch.cuda.Stream(self.device)
+            self._ev_k1 = [torch.cuda.Event(), torch.cuda.Event()]
+            self._ev_free = [torch.cuda.Event(), torch.cuda.Event()]
+        return self._dstream
+
+    def _data_begin(self, wait_for) -> int:
+        """Stream bookkeeping shared by ``data_stage`` and ``PreparedStep.launch_data``: pick the slot and make the data
+        stream wait for the inputs' producer and for the previous consumer of the slot's input buffer."""
+        d = self._overlap_state()
+        slot = self._next_slot
+        self._next_slot ^= 1
+        if wait_for is None:                 # inputs were produced on the caller's stream so far
+            wait_for = torch.cuda.Event()
+            wait_for.record(torch.cuda.current_stream(self.device))
+        if wait_for is not False:
+            d.wait_event(wait_for)
+        if self._free_valid[slot]:
+            d.wait_event(self._ev_free[slot])
+        return slot
+
+    def data_stage(self, images_u8: torch.Tensor, fwd_affine: Optional[torch.Tensor], flip: Optional[torch.Tensor] = None,
+                   wait_for=None) -> torch.Tensor:
+        """Data stage of the NEXT batch: K1 on the internal data stream into the next input slot.  ``wait_for``: a
+        torch.cuda.Event after which the images are valid (default: everything enqueued so far on the current stream;
+        ``False``: nothing to wait for -- resident inputs).  Returns the slot's input tensor; it is valid on the current
+        stream once ``loss_stage`` (or ``input_ready``) for this batch has been called."""
+        if images_u8.shape[0] != self.N:
+            raise LighthandError("HeatmapPipeline.data_stage: batch size differs from the one the pipeline was built for")
+        slot = self._data_begin(wait_for)
+        with torch.cuda.stream(self._dstream):
+            ops.warp_normalize(images_u8, fwd_affine, self.out_hw, flip=flip, mean=self.mean, std=self.std,
+                               lut=self.lut, interp=self.interp, out=self.inputs[slot], exact_norm=self.exact_norm)
+        self._ev_k1[slot].record(self._dstream)
+        self._pending.append(slot)
+        return self.inputs[slot]
+
+    def input_ready(self) -> torch.Tensor:
+        """Make the current stream wait for the oldest pending data stage and return its input tensor (what the
+        backbone reads).  ``loss_stage`` then closes that batch."""
+        if not self._pending:
+            raise LighthandError("HeatmapPipeline.input_ready: no data stage pending")
+        slot = self._pending[0]
+        torch.cuda.current_stream(self.device).wait_event(self._ev_k1[slot])
+        return self.inputs[slot]
+
+    def _loss_end(self) -> int:
+        slot = self._pending.pop(0)
+        self._ev_free[slot].record(torch.cuda.current_stream(self.device))
+        self._free_valid[slot] = True
+        return slot
+
+    def loss_stage(self, pred: torch.Tensor, joints: torch.Tensor, inv_affine: Optional[torch.Tensor] = None) -> dict:
+        """Loss stage of the CURRENT batch (the oldest pending data stage) on the current stream: waits for its K1,
+        then the fused K2+K3+K4+K5 launch.  Same outputs as ``step``."""
+        inp = self.input_ready()
+        ops.heatmap_fused(pred, joints, sigma=self.sigma, feat_stride=self.stride,
+                          want_target=self.materialize_target, want_grad=self.train, want_decode=True,
+                          out_scale=self.stride[0], subpixel=self.subpixel,
+                          inv_affine=inv_affine if self.map_back else None,
+                          loss_meter=self.meter.loss_meter, buffers=self.buffers,
+                          metrics=(self.meter.counts, self.meter.sums), pck_T=self.pck_T)
+        self._loss_end()
+        out = dict(self.buffers)
+        out["input"] = inp
+        out.pop("ws")
+        return out
+
+    def step_overlapped(self, next_images_u8, next_fwd_affine, joints, pred, next_flip=None, inv_affine=None,
+                        wait_for=None) -> dict:
+        """One iteration of the pipelined loop: data stage of the NEXT batch (pass ``next_images_u8=None`` after the
+        last one), then the loss stage of the CURRENT batch (whose data stage was the previous call's, or an explicit
+        ``data_stage`` before the loop)."""
+        if next_images_u8 is not None:
+            self.data_stage(next_images_u8, next_fwd_affine, next_flip, wait_for)
+        return self.loss_stage(pred, joints, inv_affine)
+
     def prepare(self, images_u8, fwd_affine, joints, pred, flip=None, inv_affine=None) -> "PreparedStep":
         """Validate and marshal the two C-ABI calls ONCE for a fixed set of device buffers; the returned
         object's ``launch()`` then costs two raw ctypes calls (no per-step Python argument work), which
@@ -117,10 +208,15 @@ class HeatmapPipeline:
         self.meter.reset()
 
     def metrics(self, all_reduce: bool = True) -> dict:
-        """Epoch-end read: optional cross-rank sum (the path's only collective), one D2H."""
+        """Epoch-end (or mid-epoch) read: optional cross-rank sum (the path's only collective), one D2H.
+        Idempotent: the sum is taken over copies, the local accumulators keep this rank's own totals, so a
+        second call in the same epoch does not re-reduce already-global numbers."""
         if all_reduce:
-            from .distributed import all_reduce_metrics
-            all_reduce_metrics([self.meter.counts, self.meter.sums])
+            from .distributed import all_reduce_metrics, is_initialized
+            if is_initialized():
+                counts, sums = self.meter.counts.clone(), self.meter.sums.clone()
+                all_reduce_metrics([counts, sums])
+                return self.meter.result(counts, sums)
         return self.meter.result()
 
     def algorithmic_bytes_per_image(self) -> dict:
@@ -157,8 +253,10 @@ class PreparedStep:
         self._keep = (images_u8, fwd_affine, joints, pred, flip, inv_affine, p)
         self._ms = ops._mean_std(p.mean, p.std)
         ptr = ops._ptr
-        self._k1 = (images_u8.data_ptr(), sh * sw * 3, sh, sw, sw * 3, ptr(fwd_affine), ptr(flip), None, self._ms,
-                    ptr(p.lut), p.interp, ops.LH_CHAN_RGB, ops.LH_LAYOUT_CHW, p.input.data_ptr(), n, p.out_hw[0], p.out_hw[1])
+        self._k1s = [(images_u8.data_ptr(), sh * sw * 3, sh, sw, sw * 3, ptr(fwd_affine), ptr(flip), None, self._ms,
+                      ptr(p.lut), p.interp, ops.LH_CHAN_RGB, ops.LH_LAYOUT_CHW, inp.data_ptr(), n, p.out_hw[0], p.out_hw[1])
+                     for inp in p.inputs]
+        self._k1 = self._k1s[0]
         a = _lib.HeatmapArgs()
         b = p.buffers
         table, side = ops.hrnet_table(p.sigma, p.device)
@@ -194,6 +292,26 @@ class PreparedStep:
             events[2].record()
         if rc:
             check(rc, "prepared step")
+
+    def launch_data(self) -> None:
+        """Overlapped form, data stage: K1 of THIS prepared batch on the pipeline's data stream (resident inputs:
+        nothing to wait for except the slot's previous consumer)."""
+        p = self._keep[6]
+        slot = p._data_begin(False)
+        rc = self._f1(*self._k1s[slot], p._dstream.cuda_stream)
+        if rc:
+            check(rc, "prepared step (data stage)")
+        p._ev_k1[slot].record(p._dstream)
+        p._pending.append(slot)
+
+    def launch_loss(self) -> None:
+        """Overlapped form, loss stage of THIS prepared batch on the current stream (after its ``launch_data``)."""
+        p = self._keep[6]
+        p.input_ready()
+        rc = self._f2(self._aref, torch.cuda.current_stream().cuda_stream)
+        if rc:
+            check(rc, "prepared step (loss stage)")
+        p._loss_end()
 
     def launch_split(self, stream_k1: int, stream_fused: int) -> None:
         """K1 and the fused heat-map pass touch disjoint data (images -> input; pred/joints -> grad/coords), so
@@ -308,6 +426,33 @@ class HostPipeline:
 
     def wait(self, slot: int):
         check(self.lib.lh_pipeline_wait(self._h, int(slot)), "lh_pipeline_wait")
+
+    # the two halves of ``submit`` for a host that runs the backbone in between (on ``loss_stream``)
+    def submit_inputs(self, images, fwd_affine, joints, flip=None, pred=None, out=None):
+        out = out if out is not None else self.new_outputs()
+        io = self._io(images, fwd_affine, joints, flip, pred, out)
+        slot = C.c_int(-1)
+        check(self.lib.lh_pipeline_submit_inputs(self._h, C.byref(io), C.byref(slot)), "lh_pipeline_submit_inputs")
+        return slot.value, out, (io, images, fwd_affine, joints, flip, pred)
+
+    def submit_loss(self, slot: int):
+        check(self.lib.lh_pipeline_submit_loss(self._h, int(slot)), "lh_pipeline_submit_loss")
+
+    @property
+    def loss_stream(self) -> torch.cuda.ExternalStream:
+        return torch.cuda.ExternalStream(int(self.lib.lh_pipeline_loss_stream(self._h)), device=f"cuda:{self.cfg.device}")
+
+    def input_slot(self, slot: int):
+        return self._view(self.lib.lh_pipeline_input_dev_slot(self._h, int(slot)), (self.N, 3, *self.out_hw))
+
+    def all_reduce_metrics(self, comm) -> None:
+        """SUM the context's running accumulators over the ranks of ``comm`` (distributed.MetricComm)."""
+        check(self.lib.lh_pipeline_allreduce_metrics(self._h, comm._h), "lh_pipeline_allreduce_metrics")
+
+    def read_metrics(self):
+        counts, sums = np.zeros(4, np.uint64), np.zeros(4, np.float64)
+        check(self.lib.lh_pipeline_read_metrics(self._h, counts.ctypes.data, sums.ctypes.data), "lh_pipeline_read_metrics")
+        return counts, sums
 
     def step(self, images, fwd_affine, joints, flip=None, pred=None, out=None):
         slot, out, _keep = self.submit(images, fwd_affine, joints, flip, pred, out)

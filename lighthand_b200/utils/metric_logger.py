@@ -51,10 +51,11 @@ class DeviceMeter:
     def loss_meter(self) -> torch.Tensor:
         return self.sums[1:3]
 
-    def result(self) -> dict:
-        """One synchronising read; values as the reference's meters report them."""
-        c = self.counts.cpu().tolist()
-        s = self.sums.cpu().tolist()
+    def result(self, counts: torch.Tensor = None, sums: torch.Tensor = None) -> dict:
+        """One synchronising read; values as the reference's meters report them.  ``counts`` / ``sums``:
+        all-reduced copies of the accumulators (the local ones stay per-rank; reading twice is idempotent)."""
+        c = (self.counts if counts is None else counts).cpu().tolist()
+        s = (self.sums if sums is None else sums).cpu().tolist()
         n_wrong, n_total, epe_cnt, n_img = c
         return {
             "pck": (n_total - n_wrong) / n_total if n_total else 0.0,   # pck_losses.avg

@@ -65,12 +65,42 @@ int main(int argc, char** argv) {
     memset(&io, 0, sizeof io);
     io.images = images; io.fwd_affine = affine; io.flip = flip; io.joints = joints; io.pred = pred;
     io.loss = &loss; io.coords = coords; io.maxvals = maxvals; io.counts = counts; io.sums = sums;
-    for (int rep = 0; rep < 2; ++rep) {           /* two steps: the counters accumulate */
+    for (int rep = 0; rep < 2; ++rep) {           /* two steps (a third one below): the counters accumulate */
         int slot = -1;
         rc = lh_pipeline_submit(p, &io, &slot);
         if (rc) die("lh_pipeline_submit", rc);
         rc = lh_pipeline_wait(p, slot);
         if (rc) die("lh_pipeline_wait", rc);
+    }
+    /* the split form of a step: data stage, (backbone on the loss stream), loss stage */
+    {
+        int slot = -1;
+        rc = lh_pipeline_submit_inputs(p, &io, &slot);
+        if (rc) die("lh_pipeline_submit_inputs", rc);
+        if (!lh_pipeline_loss_stream(p) || !lh_pipeline_input_dev_slot(p, slot)) die("loss stream / input slot", -2);
+        rc = lh_pipeline_submit_loss(p, slot);
+        if (rc) die("lh_pipeline_submit_loss", rc);
+        rc = lh_pipeline_wait(p, slot);
+        if (rc) die("lh_pipeline_wait (split)", rc);
+    }
+    /* K6 at world size 1: own communicator, all-reduce of the accumulators = identity */
+    int allreduce_ok = 0;
+    {
+        unsigned char id[LH_COMM_ID_BYTES];
+        void* comm = NULL;
+        unsigned long long c2[4];
+        double s2[4];
+        rc = lh_comm_unique_id(id);
+        if (rc) die("lh_comm_unique_id", rc);
+        rc = lh_comm_init(id, 1, 0, 0, &comm);
+        if (rc) die("lh_comm_init", rc);
+        rc = lh_pipeline_allreduce_metrics(p, comm);
+        if (rc) die("lh_pipeline_allreduce_metrics", rc);
+        rc = lh_pipeline_read_metrics(p, c2, s2);
+        if (rc) die("lh_pipeline_read_metrics", rc);
+        allreduce_ok = (memcmp(c2, counts, sizeof c2) == 0) && (memcmp(s2, sums, sizeof s2) == 0);
+        rc = lh_comm_destroy(comm);
+        if (rc) die("lh_comm_destroy", rc);
     }
     /* bad arguments are reported, not crashed on */
     const int e1 = lh_pipeline_submit(p, NULL, NULL);
@@ -79,9 +109,10 @@ int main(int argc, char** argv) {
     double csum = 0.0;
     for (int i = 0; i < NB * NJ * 2; ++i) csum += coords[i];
     printf("{\"loss\": %.9g, \"coords_sum\": %.9g, \"coord0\": [%.9g, %.9g], \"maxval0\": %.9g, "
-           "\"counts\": [%llu, %llu, %llu, %llu], \"epe_sum\": %.12g, \"launches\": %d, \"e1\": %d, \"e2\": %d}\n",
+           "\"counts\": [%llu, %llu, %llu, %llu], \"epe_sum\": %.12g, \"launches\": %d, \"e1\": %d, \"e2\": %d, "
+           "\"allreduce_ok\": %d}\n",
            loss, csum, coords[0], coords[1], maxvals[0], counts[0], counts[1], counts[2], counts[3], sums[0],
-           lh_pipeline_launches_per_step(p), e1, e2);
+           lh_pipeline_launches_per_step(p), e1, e2, allreduce_ok);
     lh_pipeline_destroy(p);
     free(images); free(affine); free(flip); free(joints); free(pred); free(coords); free(maxvals);
     return 0;

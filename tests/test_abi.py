@@ -26,7 +26,7 @@ def test_header_symbols_are_exported_and_bound():
 
 def test_version_and_error_text():
     lib = _lib.load()
-    assert lib.lh_abi_version() == 3
+    assert lib.lh_abi_version() == _lib.ABI_VERSION == 4
     assert b"NULL" in lib.lh_strerror(-2)
     assert lib.lh_strerror(-1).startswith(b"lighthand_b200")
     assert lib.lh_heatmap_ws_bytes(256, 21) == 16 + 24 * 256 * 21

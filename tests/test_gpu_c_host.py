@@ -47,6 +47,7 @@ def test_c_host_binds_the_abi_and_matches_the_oracle(tmp_path):
     assert got["coords_sum"] == pytest.approx(float(coords.astype(np.float64).sum()), rel=1e-9)
     assert got["coord0"] == [float(coords[0, 0, 0]), float(coords[0, 0, 1])]
     assert got["maxval0"] == pytest.approx(float(maxvals[0, 0, 0]), rel=1e-7)
-    assert got["counts"] == [2 * (total - correct), 2 * total, 2 * int(ecnt), 2 * N]      # two steps accumulated
-    assert got["epe_sum"] == pytest.approx(2 * esum, rel=1e-6)
+    assert got["counts"] == [3 * (total - correct), 3 * total, 3 * int(ecnt), 3 * N]      # three steps accumulated
+    assert got["epe_sum"] == pytest.approx(3 * esum, rel=1e-6)
+    assert got["allreduce_ok"] == 1          # lh_comm_* + lh_pipeline_allreduce_metrics at world size 1
     assert got["launches"] == 2 and got["e1"] == -2 and got["e2"] == -2                    # LH_ENULL

@@ -231,3 +231,111 @@ def test_pred_eval_reads_pred_store_json(tmp_path, monkeypatch):
     assert bar.n == 4 and np.array_equal(out["mean_auc"][2], g["mm30/mean_auc/pck_t"])
     auc, mean_px, _ = A.pred_test(types.SimpleNamespace(name="run1"), [0.1, 0.3], bar, "pckb")
     assert auc == pytest.approx(float(g["test/pckb/auc"]), rel=1e-12)
+
+
+def test_overlapped_pipeline_is_bit_identical_to_the_serial_step():
+    """data_stage / loss_stage (K1 of batch i+1 on the data stream while the loss stage of batch i runs) must give,
+    batch by batch, exactly what the serial ``step`` gives -- the two launches touch disjoint buffers."""
+    from lighthand_b200.pipeline import HeatmapPipeline
+    from lighthand_b200.utils.preprocessing import batch_patch_matrices
+    S, H, n, nb = 256, 64, 32, 5
+    batches = []
+    for b in range(nb):
+        imgs, joints, bbox, scale, rot, flip = synth(n, S, H, 2, seed=500 + b)
+        trans, _ = batch_patch_matrices(bbox, flip, scale, rot, (S, S), (S, S))
+        pred = np.random.default_rng(b).standard_normal((n, 21, H, H)).astype(np.float32)
+        batches.append([cu(imgs), cu(trans.astype(np.float64)), cu(joints), cu(pred), cu(flip.astype(np.uint8))])
+    keys = ("input", "loss", "grad", "coords", "maxvals", "argidx", "target")
+    serial = HeatmapPipeline(n, materialize_target=True)
+    want = []
+    for d in batches:
+        out = serial.step(d[0], d[1], d[2], d[3], flip=d[4])
+        want.append({k: out[k].clone() for k in keys})
+    m_want = serial.metrics(all_reduce=False)
+
+    pipe = HeatmapPipeline(n, materialize_target=True)
+    pipe.data_stage(batches[0][0], batches[0][1], batches[0][4])
+    for b, d in enumerate(batches):
+        nxt = batches[b + 1] if b + 1 < nb else None
+        out = pipe.step_overlapped(nxt[0] if nxt else None, nxt[1] if nxt else None, d[2], d[3],
+                                   next_flip=nxt[4] if nxt else None)
+        for k in keys:
+            assert torch.equal(out[k], want[b][k]), (b, k)
+    assert pipe.metrics(all_reduce=False) == m_want
+
+    # the pre-marshalled form the benchmark drives
+    pipe2 = HeatmapPipeline(n, materialize_target=True)
+    steps = [pipe2.prepare(d[0], d[1], d[2], d[3], flip=d[4]) for d in batches]
+    steps[0].launch_data()
+    for b in range(nb):
+        if b + 1 < nb:
+            steps[b + 1].launch_data()
+        steps[b].launch_loss()
+        assert torch.equal(pipe2.buffers["coords"], want[b]["coords"]) and torch.equal(pipe2.buffers["grad"], want[b]["grad"])
+        assert torch.equal(pipe2.inputs[b % 2], want[b]["input"])
+    assert pipe2.metrics(all_reduce=False) == m_want
+
+
+def test_host_pipeline_split_submit_lets_the_backbone_run_between():
+    """lh_pipeline_submit_inputs / lh_pipeline_submit_loss: a stand-in backbone enqueued on the loss stream between the
+    two halves reads the slot's input and writes pred; results equal a device pipeline fed the same pred."""
+    from lighthand_b200.pipeline import HeatmapPipeline, HostPipeline
+    from lighthand_b200.utils.preprocessing import batch_patch_matrices
+    S, H, n = 256, 64, 8
+    imgs, joints, bbox, scale, rot, flip = synth(n, S, H, 2, seed=91)
+    trans, _ = batch_patch_matrices(bbox, flip, scale, rot, (S, S), (S, S))
+    M = np.ascontiguousarray(trans.astype(np.float64))
+    fl = np.ascontiguousarray(flip.astype(np.uint8))
+    hp = HostPipeline(n)
+    slot, out, _keep = hp.submit_inputs(imgs, M, joints, flip=fl)
+    with torch.cuda.stream(hp.loss_stream):
+        inp = hp.input_slot(slot)
+        hp.pred.copy_(torch.nn.functional.avg_pool2d(inp, 4).mean(1, keepdim=True).expand(-1, 21, -1, -1))   # "backbone"
+    hp.submit_loss(slot)
+    hp.wait(slot)
+    pipe = HeatmapPipeline(n)
+    ref_in = pipe.step(cu(imgs), cu(M), cu(joints), hp.pred.clone(), flip=cu(fl))
+    assert torch.equal(hp.input_slot(slot), ref_in["input"])
+    assert out["loss"][0] == ref_in["loss"].item()
+    assert np.array_equal(out["coords"], ref_in["coords"].cpu().numpy())
+    counts, sums = hp.read_metrics()
+    m = pipe.metrics(all_reduce=False)
+    assert [int(v) for v in counts] == [m["n_wrong"], m["n_total"], m["epe_count"], n]
+    hp.close()
+
+
+@pytest.mark.parametrize("S,H,sigma,n,train", [(256, 64, 2, 256, True), (224, 56, 2, 256, False), (512, 128, 3, 128, True)])
+def test_benchmarked_variant_vs_oracle_at_full_baseline_batches(S, H, sigma, n, train):
+    """The configuration bench.py times (materialize_target=False, one-FMA normalisation, TMA-staged K1, fused pass
+    without the target store) against the CPU oracle at BASELINE.json's full batch sizes: C2 256 @ 256/64 train,
+    C3 256 @ 224/56 eval, C5 128 @ 512/128 sigma 3 train."""
+    from lighthand_b200.pipeline import HeatmapPipeline
+    from lighthand_b200.utils.preprocessing import batch_patch_matrices
+    imgs, joints, bbox, scale, rot, flip = synth(n, S, H, sigma, seed=7 * S + n)
+    trans, _ = batch_patch_matrices(bbox, flip, scale, rot, (S, S), (S, S))
+    stride = S / H
+    rng = np.random.default_rng(S)
+    tgt = np.stack([R.generate_target(j, 21, (H, H), (stride, stride), sigma)[0] for j in joints])
+    pred = (tgt + 0.1 * rng.standard_normal(tgt.shape)).astype(np.float32)
+    pipe = HeatmapPipeline(n, (S, S), (S, S), (H, H), sigma=sigma, train=train, materialize_target=False, exact_norm=False)
+    st = pipe.prepare(cu(imgs), cu(trans.astype(np.float64)), cu(joints), cu(pred), flip=cu(flip.astype(np.uint8)))
+    st.launch()
+    torch.cuda.synchronize()
+    # K1: the uint8 pixel is cv2's bit for bit; one-FMA normalisation within 2 ulp (values are O(1))
+    got_in = pipe.input.cpu().numpy()
+    for i in range(0, n, max(1, n // 16)):                    # the oracle's per-sample warp costs ~10 ms: check every 16th image
+        want_chw, _, _ = R.warp_normalize_sample(imgs[i], bbox[i], bool(flip[i]), float(scale[i]), float(rot[i]), (S, S))
+        assert np.abs(got_in[i] - want_chw).max() <= 5e-7, i
+    loss, grad = R.joints_mse_loss_and_grad(pred, tgt) if train else (float(R.joints_mse_loss(pred, tgt)), None)
+    coords, maxvals, idx = R.decode_final(pred, stride)
+    correct, total = R.pck_2d_counts(coords, joints, 0.2, "proportion")
+    esum, ecnt = R.epe_train(coords, joints)
+    assert pipe.buffers["loss"].item() == pytest.approx(loss, rel=1e-5)
+    if train:
+        np.testing.assert_allclose(pipe.buffers["grad"].cpu().numpy(), grad, rtol=1e-5, atol=1e-12)
+    assert np.array_equal(pipe.buffers["argidx"].cpu().numpy(), idx)
+    assert np.array_equal(pipe.buffers["coords"].cpu().numpy(), coords)
+    assert np.array_equal(pipe.buffers["maxvals"].cpu().numpy(), maxvals)
+    m = pipe.metrics(all_reduce=False)
+    assert (m["n_total"] - m["n_wrong"], m["n_total"], m["epe_count"]) == (correct, total, ecnt)
+    assert m["epe_sum"] == pytest.approx(esum, rel=1e-6)

@@ -135,3 +135,44 @@ def test_resize_224_to_256_vs_oracle(ops):
     out = ops.warp_normalize(cu(imgs), None, (256, 256), interp=ops.LH_INTERP_TORCH).cpu().numpy()
     for i in range(2):
         np.testing.assert_allclose(out[i], R.resize_normalize_sample(imgs[i], (256, 256)), rtol=1e-5, atol=1e-5)
+
+
+def test_tma_kernel_and_record_kernel_agree_bit_for_bit(tmp_path):
+    """The TMA-staged persistent kernel (default for 16-byte aligned rows) and the record-staging kernel it replaced
+    (LH_K1=records, also the path for unaligned pitches) must produce identical floats: tiles sticking out of the source,
+    tiles missing it altogether, flips, the three normalisation modes, a 2-image tail batch."""
+    import json, os, subprocess, sys
+    from conftest import ROOT
+    code = r'''
+import sys, json, hashlib
+import numpy as np, torch
+sys.path.insert(0, %r)
+from lighthand_b200 import ops
+from oracle import restate as R
+rng = np.random.default_rng(5)
+res = {}
+for S, n in ((256, 7), (224, 2), (512, 3)):
+    imgs = rng.integers(0, 256, (n, S, S, 3), dtype=np.uint8)
+    Ms, fl = [], []
+    for i in range(n):
+        side = S * rng.uniform(0.5, 1.6)                      # crops larger than the image: borders and all-outside tiles
+        cx, cy = S / 2 + rng.uniform(-S / 3, S / 3), S / 2 + rng.uniform(-S / 3, S / 3)
+        Ms.append(R.gen_trans_from_patch_cv(cx, cy, side, side, S, S, rng.uniform(0.75, 1.25), rng.uniform(-90, 90)).astype(np.float64))
+        fl.append(rng.uniform() < 0.5)
+    d = torch.from_numpy(imgs).cuda(); M = torch.from_numpy(np.stack(Ms)).cuda(); f = torch.from_numpy(np.array(fl, np.uint8)).cuda()
+    for tag, kw in (("lut", dict(exact_norm=True)), ("fma", dict(exact_norm=False)), ("raw", dict(mean=None, std=None))):
+        out = ops.warp_normalize(d, M, (S, S), flip=f, **kw)
+        res["%%d_%%s" %% (S, tag)] = hashlib.sha256(out.cpu().numpy().tobytes()).hexdigest()
+    want = np.stack([R.warp_affine_model(imgs[i], Ms[i], S, S, flip=bool(fl[i])) for i in range(n)]).astype(np.float32)
+    raw = ops.warp_normalize(d, M, (S, S), flip=f, mean=None, std=None, layout=ops.LH_LAYOUT_HWC).cpu().numpy()
+    res["%%d_model" %% S] = bool(np.array_equal(raw, want))
+print(json.dumps(res))
+''' % ROOT
+    outs = []
+    for variant in ("", "records"):
+        env = dict(os.environ, LH_K1=variant)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    assert outs[0] == outs[1]
+    assert all(v is True for k, v in outs[0].items() if k.endswith("_model"))

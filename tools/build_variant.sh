@@ -6,9 +6,9 @@ set -e
 tag=$1; shift
 cd "$(dirname "$0")/../lighthand_b200/csrc"
 mkdir -p build/var_$tag
-for f in capi heatmap metrics warp_normalize warp_tma frei_crop color_jitter pipeline; do
+for f in capi heatmap metrics warp_normalize warp_tma frei_crop color_jitter pipeline comm; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC $@ -c $f.cu -o build/var_$tag/$f.o &
 done
 wait
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../variants_$tag.so build/var_$tag/*.o -cudart static
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../variants_$tag.so build/var_$tag/*.o -cudart static -ldl
 echo built variants_$tag.so
