@@ -101,7 +101,8 @@ int lh_gen_targets(const float* joints, int joint_stride /*floats per joint: 2 o
  * K3  JointsMSELoss forward + backward.   Replaces src/utils/loss.py:306-325 (+ autograd backward).
  * loss = 0.5/(N*J*HW) * sum((pred*w - target*w)^2), w = weight[n,j] or 1 (the reference ignores
  * target_weight: pass NULL).  grad (nullable) = d loss / d pred.  loss_f64 / loss_f32: dev [1], nullable.
- * ws: dev workspace of lh_heatmap_ws_bytes(N,J) bytes, zero-initialised ONCE by the caller (the
+ * ws: dev workspace of lh_heatmap_ws_bytes(N,J) bytes (per-CTA partial slots + the words through which the pieces of
+ * a split map meet), zero-initialised ONCE by the caller (the
  * kernels leave it zeroed again).
  * ------------------------------------------------------------------------------------------ */
 size_t lh_heatmap_ws_bytes(int64_t N, int J);

@@ -18,13 +18,14 @@
 // into the running metric accumulators -- so a whole step's post-backbone work is ONE launch.
 // HBM-bound by construction: it moves H*W*4 B in (+ H*W*4 B per requested output).
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 
 #include "lh_common.cuh"
 
 namespace lh {
 
 constexpr int kThreads = 256;      // scalar kernel
-constexpr int kVecThreads = 128;   // vector kernel: 4 warps per map, 8 CTAs per SM
 constexpr int kMaxTable = 31 * 31;
 
 struct HeatmapParams {
@@ -49,6 +50,11 @@ struct HeatmapParams {
     double* cta_loss;           // ws + 16: one slot per CTA (sum of its maps' squared-error sums, in map order)
     double* cta_epe;            // per CTA: sum of float32 distances of joints 1..J-2
     unsigned int* cta_wrong;    // per CTA: number of failed PCK tests
+    unsigned long long* map_key; // per map: (order key << 32 | ~index) of split maps (zero between launches)
+    unsigned int* map_cnt;      // per map: pieces arrived
+    long long n_full, units;    // whole-map units, all units (work list of heatmap_warp_kernel)
+    int P, WR;                  // pieces per remaining map, warp-rows (32 float4) per map
+    unsigned int vinv;          // ceil(2^20 / (W/4)): v / (W/4) == (v * vinv) >> 20
     long long n_maps;
     int J, H, W, HW;
     int joint_stride, side, style, use_weight, subpixel;
@@ -254,243 +260,247 @@ __device__ __forceinline__ void final_reduce(const HeatmapParams& p, bool do_met
     }
 }
 
+// The map's tail as a separate function (its registers -- FP64 inverse affine, bbox reduction -- stay out of the
+// streaming loop's allocation).  Whole warp; the joints were fetched at the head of the unit.
+__device__ __noinline__ void finish_map(const HeatmapParams& p, long long m, int bi, float mv, bool do_metric, float2 jl,
+                                        float2 jfirst, float2 gj, int lane, double& epe_acc, unsigned int& wrong_acc) {
+    if (bi == 0x7fffffff) bi = 0;    // HW == 0 only
+    map_tail(p, m, p.pred + (size_t)m * p.HW, bi, mv, do_metric, jl, jfirst, gj, lane, epe_acc, wrong_acc);
+}
+
 // ------------------------------------------------------------------------------------------------
-// Vectorised persistent kernel.  TSRC: 0 = no target (decode only), 1 = generate from joints, 2 = read
-// target_in.  FLAGS (compile time, so absent outputs cost nothing): F_GRAD write d loss / d pred,
-// F_TOUT write the target, F_DEC argmax decode, F_WGT per-map weights.
-// Each CTA walks maps m = blockIdx.x, += gridDim.x; per map two barriers:
-//   A  after the streaming pass: per-warp loss partial + NaN-propagating maximum
-//   B  after the winner search: smallest index holding the maximum (numpy's first-index tie-break)
-// Warp 0 then finishes the map (coordinates, outputs, metric record) while the other warps are already
-// streaming the next one; reduction scratch is triple-buffered by map count (see s_sum below).
+// Vectorised persistent kernel, ONE WARP PER MAP.  TSRC: 0 = no target (decode only), 1 = generate from joints,
+// 2 = read target_in.  FLAGS (compile time, so absent outputs cost nothing): F_GRAD write d loss / d pred, F_TOUT
+// write the target, F_DEC argmax decode, F_WGT per-map weights.
+//
+// A warp streams a map as "warp-rows" of 32 float4 (512 contiguous bytes per load instruction), kU of them in flight
+// per lane; loss partial, maximum and first index are reduced with shuffles / REDUX inside the warp and the same warp
+// finishes the map (coordinates, PCK / EPE record).  No block barrier and no shared-memory exchange per map -- the
+// CTA-per-map version of round 1 spent its time in exactly that chain (stream -> reduce -> barrier -> winner search
+// -> barrier) and lost a row group whenever H was not a multiple of its rows-per-pass (56 x 56).  Any H x W with
+// W % 4 == 0 streams at the same rate here.
+//
+// Work list (static, interleaved over the CTAs): with Wt resident warps, the first floor(n_maps / Wt) * Wt maps are
+// whole-map units; the REMAINING maps are cut into P = floor(Wt / remaining) pieces of consecutive warp-rows so that
+// the last round keeps every warp busy for 1/P of a map instead of leaving most of them idle (batch 256 x 21 joints
+// on 4736 warps: 4736 whole maps + 640 maps in 7 pieces).  Pieces of one map meet through the workspace: a 64-bit
+// atomicMax on (order key << 32 | ~index) -- maximum value first, then the smallest index = numpy's tie-break -- and a
+// counter; the piece that arrives last finishes the map and leaves both words zeroed.  Loss partials never meet per
+// map: every unit adds to its warp's float64 sum, warps are combined per CTA in warp order, CTAs by the last CTA in
+// index order -> deterministic loss for a given grid.
 // ------------------------------------------------------------------------------------------------
 constexpr int F_GRAD = 1, F_TOUT = 2, F_DEC = 4, F_WGT = 8;
+constexpr int kWarpsPerCta = 8;
+constexpr int kWarpThreads = 32 * kWarpsPerCta;
 
+#ifndef LH_HM_MINB
+#define LH_HM_MINB 3
+#endif
 template <bool PRED, int TSRC, int FLAGS>
-struct VecBody {
-    static constexpr bool GRAD = (FLAGS & F_GRAD) != 0, TOUT = (FLAGS & F_TOUT) != 0, DEC = (FLAGS & F_DEC) != 0,
-                          WGT = (FLAGS & F_WGT) != 0, LOSS = PRED && TSRC != 0;
-    // one 4-float vector at element offset e of the current map (row y, fixed column group)
-    __device__ static __forceinline__ void run(const float4& pv, const float4& tv, int y, int e, const Window& win,
-                                               const float* s_tab, int side, const int (&tx)[4], const bool (&xin)[4],
-                                               bool any_x, float wgt, float gs, float* tout, float* grad,
-                                               float& acc0, float& acc1, float& tmax, int& tvec) {
-        float t[4] = {0.f, 0.f, 0.f, 0.f};
-        if (TSRC == 1) {
-            const unsigned ry = (unsigned)(y - win.uly);
-            if (any_x && ry < (unsigned)(win.bry - win.uly)) {
-                const float* trow = s_tab + ry * side;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) if (xin[k]) t[k] = trow[tx[k]];
-            }
-            if (TOUT) stg_stream4(tout + e, make_float4(t[0], t[1], t[2], t[3]));
-        } else if (TSRC == 2) {
-            t[0] = tv.x; t[1] = tv.y; t[2] = tv.z; t[3] = tv.w;
-        }
-        if (PRED) {
-            const float v[4] = {pv.x, pv.y, pv.z, pv.w};
-            if (LOSS) {
-                float d[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) d[k] = WGT ? (v[k] - t[k]) * wgt : (v[k] - t[k]);
-                acc0 = fmaf(d[0], d[0], acc0); acc1 = fmaf(d[1], d[1], acc1);
-                acc0 = fmaf(d[2], d[2], acc0); acc1 = fmaf(d[3], d[3], acc1);
-                if (GRAD) stg_cs4(grad + e, make_float4(d[0] * gs, d[1] * gs, d[2] * gs, d[3] * gs));
-            }
-            if (DEC) {
-                // vectors are visited in increasing index order: replace only on "strictly greater", or when
-                // the first NaN shows up (NaN is numpy's maximum); never once tmax is NaN.
-                const float vmax = max_nan(max_nan(v[0], v[1]), max_nan(v[2], v[3]));
-                const bool upd = !(vmax <= tmax) && (tmax == tmax);
-                tmax = upd ? vmax : tmax;
-                tvec = upd ? e : tvec;
-            }
-        }
-    }
-};
-
-template <bool PRED, int TSRC, int FLAGS>
-__global__ void __launch_bounds__(kVecThreads, TSRC == 2 ? 4 : 8) heatmap_vec_kernel(const HeatmapParams p) {
-    using Body = VecBody<PRED, TSRC, FLAGS>;
-    constexpr bool GRAD = Body::GRAD, TOUT = Body::TOUT, DEC = Body::DEC, WGT = Body::WGT, LOSS = Body::LOSS;
+__global__ void __launch_bounds__(kWarpThreads, TSRC == 2 ? 3 : LH_HM_MINB) heatmap_warp_kernel(const __grid_constant__ HeatmapParams p) {
+    constexpr bool GRAD = (FLAGS & F_GRAD) != 0, TOUT = (FLAGS & F_TOUT) != 0, DEC = PRED && (FLAGS & F_DEC) != 0,
+                   WGT = (FLAGS & F_WGT) != 0, LOSS = PRED && TSRC != 0;
+    constexpr int kU = (TSRC == 2) ? 2 : 4;        // float4 per buffer; two buffers (one in flight, one being consumed)
     __shared__ float s_tab[TSRC == 1 ? kMaxTable : 1];
-    // reduction scratch, TRIPLE-buffered by map count: after barrier A of map i warp 0 still reads map i-1's slots
-    // ("finish the previous map one barrier late") while the other warps already write map i+1's
-    __shared__ double s_sum[3][kVecThreads / kWarp];
-    __shared__ __align__(16) float s_max[3][kVecThreads / kWarp];
-    __shared__ __align__(16) int s_idx[3][kVecThreads / kWarp];
-    static_assert(kVecThreads / kWarp == 4, "the float4 / int4 reads of s_max / s_idx assume 4 warps");
-    __shared__ double s_fin[kVecThreads / kWarp];
-    __shared__ unsigned int s_finc[kVecThreads / kWarp];
+    __shared__ double s_wl[kWarpsPerCta], s_we[kWarpsPerCta];
+    __shared__ unsigned int s_ww[kWarpsPerCta];
+    __shared__ double s_fa[kWarpsPerCta], s_fb[kWarpsPerCta];
+    __shared__ unsigned int s_fc[kWarpsPerCta];
     __shared__ int s_last;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     if (TSRC == 1) {
-        for (int i = tid; i < p.side * p.side; i += kVecThreads) s_tab[i] = p.table[i];
+        for (int i = tid; i < p.side * p.side; i += kWarpThreads) s_tab[i] = p.table[i];
         __syncthreads();
     }
     const bool do_metric = DEC && p.metric_counts != nullptr;
-
-    constexpr int U = 4;
-    const int W = p.W, H = p.H, side = p.side;
-    const int vw = W >> 2;                   // vectors per row (<= 256, checked by the launcher)
-    const int rp = kVecThreads / vw;            // rows per pass
-    const int r0 = tid / vw, c = tid - r0 * vw;
-    const int x = 4 * c;
-    const bool active = r0 < rp;
-    const int e0 = r0 * W + x;               // first element of this thread, estep elements between its rows
-    const int estep = rp * W;
-    const int G = (H + U * rp - 1) / (U * rp);   // groups of U rows-per-thread in one map
+    const int W = p.W, side = p.side, V = p.HW >> 2, vw = W >> 2;
     const float ninf = __int_as_float(0xff800000);
+    const int Wt = (int)gridDim.x * kWarpsPerCta;                       // (the launcher keeps units below 2^31)
+    const int wid = warp * (int)gridDim.x + (int)blockIdx.x;            // consecutive units land on different SMs
+    const int n_full = (int)p.n_full, units = (int)p.units;
 
-    __shared__ double s_cta[2];              // running sums of this CTA (thread 0): squared error, EPE distances
-    __shared__ unsigned int s_ctaw;          // failed PCK tests
-    if (tid == 0) { s_cta[0] = 0.0; s_cta[1] = 0.0; s_ctaw = 0u; }
+    double loss_acc = 0.0, epe_acc = 0.0;          // this warp's running sums (lane 0)
+    unsigned int wrong_acc = 0u;
 
-    // software pipeline: the loads of work item k+1 (next row group, possibly of the next map) are issued
-    // right after item k's registers are consumed, so they are in flight across the reductions, the barrier
-    // and the tail of the map.  The tail of map i runs after barrier A of map i+1 (one barrier per map).
-    float4 pv[U], tv[U];
-#define LH_ISSUE(MM, GG)                                                                        \
-    {                                                                                           \
-        const size_t base_ = (size_t)(MM) * p.HW + e0 + (GG) * U * estep;                       \
-        const int y_ = r0 + (GG) * U * rp;                                                      \
-        _Pragma("unroll") for (int u = 0; u < U; ++u) {                                         \
-            if (active && y_ + u * rp < H) {                                                    \
-                if (PRED) pv[u] = ldg_stream4(p.pred + base_ + u * estep);                      \
-                if (TSRC == 2) tv[u] = ldg_stream4(p.target_in + base_ + u * estep);            \
-            }                                                                                   \
-        }                                                                                       \
-    }
-    // warp 0: finish map PM (its reductions are visible: a barrier has passed); joints are re-read (L2 hits)
-#define LH_FINISH_PREV(PM, PPAR)                                                                \
-    {                                                                                           \
-        if (LOSS && lane == 0) {                                                                \
-            double sacc = 0.0;                                                                  \
-            _Pragma("unroll") for (int w = 0; w < kVecThreads / kWarp; ++w) sacc += s_sum[PPAR][w]; \
-            s_cta[0] += sacc;                                                                   \
-        }                                                                                       \
-        if (DEC) {                                                                              \
-            const float4 ma = *reinterpret_cast<const float4*>(&s_max[PPAR][0]);                \
-            const float Mp = max_nan(max_nan(ma.x, ma.y), max_nan(ma.z, ma.w));                 \
-            const int4 ia = *reinterpret_cast<const int4*>(&s_idx[PPAR][0]);                    \
-            int bi = min(min(ia.x, ia.y), min(ia.z, ia.w));                                     \
-            if (bi == 0x7fffffff) bi = 0; /* HW == 0 only */                                    \
-            float2 pgj = make_float2(0.f, 0.f), pjl = pgj, pjfirst = pgj;                       \
-            if (do_metric) {                                                                    \
-                const float* jp_ = p.joints + (PM) * p.joint_stride;                            \
-                pgj = make_float2(jp_[0], jp_[1]);                                              \
-                const float* gp_ = p.joints + ((PM) / p.J) * p.J * p.joint_stride;              \
-                pjfirst = make_float2(gp_[0], gp_[1]);                                          \
-                if (lane < p.J && p.J <= 32) pjl = make_float2(gp_[lane * p.joint_stride], gp_[lane * p.joint_stride + 1]); \
-            }                                                                                   \
-            double epe_ = 0.0; unsigned int wr_ = 0u;                                           \
-            map_tail(p, (PM), p.pred + (size_t)(PM) * p.HW, bi, Mp, do_metric, pjl, pjfirst, pgj, lane, epe_, wr_); \
-            if (lane == 0 && do_metric) { s_cta[1] += epe_; s_ctaw += wr_; }                    \
-        }                                                                                       \
-    }
-
-    long long m = blockIdx.x, pm = -1;
-    int g = 0, par = 0;
-    if (m < p.n_maps) LH_ISSUE(m, 0)
-
-    // state of the map being streamed
-    int ulx = 0, uly = 0, brx = 0, bry = 0;
-    float wgt = 1.0f, gs = p.grad_scale;
-    float acc0 = 0.f, acc1 = 0.f, tmax = ninf;
-    int tvec = e0;
-
-    while (m < p.n_maps) {
-        if (g == 0) {
-            // ---- per-map setup -------------------------------------------------------------------------
-            ulx = uly = brx = bry = 0;
-            bool valid = false;
-            if (TSRC == 1) {
-                const float* jp = p.joints + m * p.joint_stride;
-                const Window win = joint_window(p, jp[0], jp[1]);
-                valid = win.valid != 0;
-                if (valid) { ulx = win.ulx; uly = win.uly; brx = win.brx; bry = win.bry; }
-                if (p.weight_out && tid == 0) p.weight_out[m] = valid ? 1.0f : 0.0f;
-            }
-            if (WGT) {
-                wgt = 1.0f;
-                if (p.weight_in) wgt = p.weight_in[m];
-                else if (TSRC == 1) wgt = valid ? 1.0f : 0.0f;
-                gs = p.grad_scale * wgt;                         // grad = (pw - tw) * w / count
-            }
-            acc0 = acc1 = 0.f; tmax = ninf; tvec = e0;
+    for (int u = wid; u < units; u += Wt) {
+        int m, k = 0, Pm = 1;
+        if (u < n_full) {
+            m = u;
+        } else {
+            const int r = u - n_full, q = r / p.P;
+            m = n_full + q; k = r - q * p.P; Pm = p.P;
         }
-        // ---- consume the group in registers ----------------------------------------------------------------
-        if (active) {
-            Window win;
-            win.ulx = ulx; win.uly = uly; win.brx = brx; win.bry = bry; win.valid = 1;
-            int tx[4];
-            bool xin[4], any_x = false;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {                        // x part of the Gaussian window test
-                tx[k] = x + k - ulx;
-                xin[k] = (TSRC == 1) && (x + k >= ulx) && (x + k < brx);
-                any_x |= xin[k];
-            }
-            const size_t base = (size_t)m * p.HW;
-            float* tout = TOUT ? p.target_out + base : nullptr;
-            float* grad = GRAD ? p.grad + base : nullptr;
-            const int y = r0 + g * U * rp, e = e0 + g * U * estep;
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (y + u * rp < H)
-                    Body::run(pv[u], tv[u], y + u * rp, e + u * estep, win, s_tab, side, tx, xin, any_x, wgt, gs,
-                              tout, grad, acc0, acc1, tmax, tvec);
-        }
-        // ---- issue the next item's loads ---------------------------------------------------------------------
-        long long m2 = m;
-        int g2 = g + 1;
-        if (g2 == G) { g2 = 0; m2 = m + gridDim.x; }
-        if (m2 < p.n_maps) LH_ISSUE(m2, g2)
+        const int wr0 = (int)(((long long)k * p.WR) / Pm), wr1 = (int)(((long long)(k + 1) * p.WR) / Pm);
 
-        if (g2 == 0 && PRED) {
-            // ---- map finished: warp partials, barrier A, winner search ---------------------------------------
-            float wsum = acc0 + acc1, wmax = tmax;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                if (LOSS) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
-                if (DEC) wmax = max_nan(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-            }
-            if (lane == 0) { if (LOSS) s_sum[par][warp] = (double)wsum; if (DEC) s_max[par][warp] = wmax; }
-            __syncthreads();
-            // the barrier also published the previous map's winner indices: warp 0 finishes that map now
-            if (warp == 0 && pm >= 0) LH_FINISH_PREV(pm, (par + 2) % 3)
-            if (DEC) {
-                const float4 ma = *reinterpret_cast<const float4*>(&s_max[par][0]);
-                const float M = max_nan(max_nan(ma.x, ma.y), max_nan(ma.z, ma.w));
-                const bool mnan = M != M;
-                int cand = 0x7fffffff;
-                // threads whose own maximum IS the map maximum look up its first position inside their vector
-                // (threads that own no row of a map with H < rows-per-pass keep tvec outside the map: r0 < H)
-                if (active && r0 < H && (mnan ? (tmax != tmax) : (tmax == M))) {
-                    const float4 q = *reinterpret_cast<const float4*>(p.pred + (size_t)m * p.HW + tvec);
-                    const float v[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                    for (int k = 3; k >= 0; --k) if (mnan ? (v[k] != v[k]) : (v[k] == M)) cand = tvec + k;
+        const size_t base = (size_t)m * p.HW;
+        const float* pred = PRED ? p.pred + base : nullptr;
+        const float* tin = (TSRC == 2) ? p.target_in + base : nullptr;
+        float* tout = TOUT ? p.target_out + base : nullptr;
+        float* grad = GRAD ? p.grad + base : nullptr;
+        const int vend = min(wr1 * 32, V);                      // this lane streams vectors v = wr * 32 + lane < vend
+
+        // ---- software pipeline: two buffers of kU vectors; the first chunk's loads go out BEFORE anything that
+        // depends on the joints (a warp owns little more than one map: every dependent global round trip at the head or
+        // the tail of a unit would be paid in full) ---------------------------------------------------------------
+        float4 pa[kU], pb[kU], ta[kU], tb[kU];
+#define LH_LOAD(PV, TV, WRB)                                                        \
+        _Pragma("unroll") for (int i = 0; i < kU; ++i) {                            \
+            const int v_ = ((WRB) + i) * 32 + lane;                                 \
+            if (v_ < vend) {                                                        \
+                if (PRED) PV[i] = ldg_stream4(pred + 4 * v_);                       \
+                if (TSRC == 2) TV[i] = ldg_stream4(tin + 4 * v_);                   \
+            }                                                                       \
+        }
+        LH_LOAD(pa, ta, wr0)
+
+        // ---- per-map setup: ONE coalesced load brings the sample's J ground-truth joints (lane = joint); the map's own
+        // joint (window, PCK / EPE record) and the first joint (bbox quirk) come out of it by shuffle ----------------
+        float2 jl = make_float2(0.f, 0.f), gj = jl, jfirst = jl;
+        const bool need_j = (TSRC == 1) || do_metric;
+        if (need_j) {
+            const int jm = m % p.J;
+            if (p.J <= 32) {
+                if (lane < p.J) {
+                    const float* gp = p.joints + ((long long)(m - jm) + lane) * p.joint_stride;
+                    jl = make_float2(gp[0], gp[1]);
                 }
-                cand = __reduce_min_sync(0xffffffffu, cand);
-                if (lane == 0) s_idx[par][warp] = cand;
+                gj = make_float2(__shfl_sync(0xffffffffu, jl.x, jm), __shfl_sync(0xffffffffu, jl.y, jm));
+                jfirst = make_float2(__shfl_sync(0xffffffffu, jl.x, 0), __shfl_sync(0xffffffffu, jl.y, 0));
+            } else {
+                const float* jp = p.joints + (long long)m * p.joint_stride;
+                const float* gp = p.joints + (long long)(m - jm) * p.joint_stride;
+                gj = make_float2(jp[0], jp[1]);
+                jfirst = make_float2(gp[0], gp[1]);
             }
-            pm = m;
-            par = (par + 1) % 3;
         }
-        m = m2; g = g2;
+        int ulx = 0, uly = 0, wwin = 0, hwin = 0;
+        float wgt = 1.0f, gs = p.grad_scale;
+        if (TSRC == 1) {
+            const Window win = joint_window(p, gj.x, gj.y);
+            const bool valid = win.valid != 0;
+            if (valid) { ulx = win.ulx; uly = win.uly; wwin = win.brx - win.ulx; hwin = win.bry - win.uly; }
+            if (p.weight_out && lane == 0 && k == 0) p.weight_out[m] = valid ? 1.0f : 0.0f;
+            if (WGT && !p.weight_in) wgt = valid ? 1.0f : 0.0f;
+        }
+        if (WGT) {
+            if (p.weight_in) wgt = p.weight_in[m];
+            gs = p.grad_scale * wgt;                             // grad = (pw - tw) * w / count
+        }
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f, tmax = ninf;
+        int tvec = -1;                                           // element offset of the vector holding tmax (-1: none seen)
+
+#define LH_CONSUME(PV, TV, WRB)                                                                             \
+        _Pragma("unroll") for (int i = 0; i < kU; ++i) {                                                    \
+            const int v = ((WRB) + i) * 32 + lane;                                                          \
+            if (v < vend) {                                                                                 \
+                const int e = 4 * v;                                                                        \
+                float t[4] = {0.f, 0.f, 0.f, 0.f};                                                          \
+                if (TSRC == 1) {                                                                            \
+                    const int y = (int)(((unsigned)v * p.vinv) >> 20);   /* v / vw (exact: launcher checks) */ \
+                    const int x = 4 * (v - y * vw);                                                         \
+                    const unsigned ry = (unsigned)(y - uly);                                                \
+                    if (ry < (unsigned)hwin && x + 3 >= ulx && x < ulx + wwin) {                            \
+                        const float* trow = s_tab + ry * side;                                              \
+                        _Pragma("unroll") for (int c = 0; c < 4; ++c) {                                     \
+                            const unsigned xx = (unsigned)(x + c - ulx);                                    \
+                            if (xx < (unsigned)wwin) t[c] = trow[xx];                                       \
+                        }                                                                                   \
+                    }                                                                                       \
+                    if (TOUT) stg_stream4(tout + e, make_float4(t[0], t[1], t[2], t[3]));                   \
+                } else if (TSRC == 2) {                                                                     \
+                    t[0] = TV[i].x; t[1] = TV[i].y; t[2] = TV[i].z; t[3] = TV[i].w;                         \
+                }                                                                                           \
+                if (PRED) {                                                                                 \
+                    const float q[4] = {PV[i].x, PV[i].y, PV[i].z, PV[i].w};                                \
+                    if (LOSS) {                                                                             \
+                        float d[4];                                                                         \
+                        _Pragma("unroll") for (int c = 0; c < 4; ++c) d[c] = WGT ? (q[c] - t[c]) * wgt : (q[c] - t[c]); \
+                        acc0 = fmaf(d[0], d[0], acc0); acc1 = fmaf(d[1], d[1], acc1);                       \
+                        acc2 = fmaf(d[2], d[2], acc2); acc3 = fmaf(d[3], d[3], acc3);                       \
+                        if (GRAD) stg_cs4(grad + e, make_float4(d[0] * gs, d[1] * gs, d[2] * gs, d[3] * gs)); \
+                    }                                                                                       \
+                    if (DEC) {                                                                              \
+                        /* a lane visits its vectors in increasing index order: replace only on "strictly greater", or */ \
+                        /* when the first NaN shows up (NaN is numpy's maximum); never once tmax is NaN */     \
+                        const float vmax = max_nan(max_nan(q[0], q[1]), max_nan(q[2], q[3]));               \
+                        const bool upd = (tvec < 0) || (!(vmax <= tmax) && (tmax == tmax));                 \
+                        tmax = upd ? vmax : tmax;                                                           \
+                        tvec = upd ? e : tvec;                                                              \
+                    }                                                                                       \
+                }                                                                                           \
+            }                                                                                               \
+        }
+
+        // ---- stream the unit's warp-rows: chunk c+1 in flight while chunk c is consumed -------------------------
+        for (int wr = wr0; wr < wr1; wr += 2 * kU) {
+            LH_LOAD(pb, tb, wr + kU)
+            LH_CONSUME(pa, ta, wr)
+            LH_LOAD(pa, ta, wr + 2 * kU)
+            LH_CONSUME(pb, tb, wr + kU)
+        }
+#undef LH_LOAD
+#undef LH_CONSUME
+        if (!PRED) continue;
+
+        // ---- warp reductions ------------------------------------------------------------------------------------
+        if (LOSS) {
+            const double ws = warp_sum((double)(acc0 + acc1) + (double)(acc2 + acc3));
+            loss_acc += ws;                                      // every lane holds the sum; lane 0's copy is the one used
+        }
+        if (DEC) {
+            const uint32_t key = tvec >= 0 ? order_key(tmax) : 0u;
+            const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
+            // lanes whose own maximum IS the unit's maximum look up its first position inside their vector
+            int cand = 0x7fffffff;
+            float cval = 0.f;
+            if (tvec >= 0 && key == kmax) {
+                const float4 q4 = *reinterpret_cast<const float4*>(pred + tvec);
+                const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                for (int c = 3; c >= 0; --c) if (order_key(q[c]) == kmax) { cand = tvec + c; cval = q[c]; }
+            }
+            int bi = __reduce_min_sync(0xffffffffu, cand);
+            const unsigned owner = __ballot_sync(0xffffffffu, cand == bi);
+            float mv = __shfl_sync(0xffffffffu, cval, __ffs(owner) - 1);
+            bool finish = true;
+            if (Pm > 1) {
+                // pieces of one map meet in the workspace; the last one to arrive finishes the map
+                int last = 0;
+                if (lane == 0) {
+                    const unsigned long long k64 = ((unsigned long long)kmax << 32) | (unsigned long long)(0xffffffffu - (unsigned)bi);
+                    atomicMax(p.map_key + m, k64);
+                    __threadfence();
+                    const unsigned int old = atomicAdd(p.map_cnt + m, 1u);
+                    if (old == (unsigned)(Pm - 1)) {
+                        __threadfence();
+                        const unsigned long long kk = atomicExch(p.map_key + m, 0ull);   // leave the workspace zeroed
+                        p.map_cnt[m] = 0u;
+                        bi = (int)(0xffffffffu - (unsigned)(kk & 0xffffffffull));
+                        mv = __ldcg(pred + bi);
+                        last = 1;
+                    }
+                }
+                last = __shfl_sync(0xffffffffu, last, 0);
+                bi = __shfl_sync(0xffffffffu, bi, 0);
+                mv = __shfl_sync(0xffffffffu, mv, 0);
+                finish = last != 0;
+            }
+            if (finish) finish_map(p, m, bi, mv, do_metric, jl, jfirst, gj, lane, epe_acc, wrong_acc);
+        }
     }
 
     if (!PRED) return;
-    __syncthreads();                                  // publishes the last map's winner indices
-    if (warp == 0 && pm >= 0) LH_FINISH_PREV(pm, (par + 2) % 3)
-#undef LH_ISSUE
-#undef LH_FINISH_PREV
     if ((LOSS && (p.loss_f64 || p.loss_f32 || p.loss_meter)) || do_metric) {
+        if (lane == 0) { s_wl[warp] = loss_acc; s_we[warp] = epe_acc; s_ww[warp] = wrong_acc; }
+        __syncthreads();
         if (tid == 0) {
-            p.cta_loss[blockIdx.x] = s_cta[0]; p.cta_epe[blockIdx.x] = s_cta[1]; p.cta_wrong[blockIdx.x] = s_ctaw;
+            double cl = 0.0, ce = 0.0;
+            unsigned int cw = 0u;
+#pragma unroll
+            for (int w = 0; w < kWarpsPerCta; ++w) { cl += s_wl[w]; ce += s_we[w]; cw += s_ww[w]; }
+            p.cta_loss[blockIdx.x] = cl; p.cta_epe[blockIdx.x] = ce; p.cta_wrong[blockIdx.x] = cw;
             __threadfence();
             const unsigned int t = atomicAdd(p.ticket, 1u);
             s_last = (t == gridDim.x - 1);
@@ -498,7 +508,7 @@ __global__ void __launch_bounds__(kVecThreads, TSRC == 2 ? 4 : 8) heatmap_vec_ke
         __syncthreads();
         if (s_last) {
             __threadfence();
-            final_reduce<LOSS, kVecThreads>(p, do_metric, s_sum[0], s_fin, s_finc, tid);
+            final_reduce<LOSS, kWarpThreads>(p, do_metric, s_fa, s_fb, s_fc, tid);
         }
     }
 }
@@ -631,19 +641,48 @@ static int persistent_grid(K kernel, int* cache) {
     int dev = 0, sms = 0, occ = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kVecThreads, 0) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kWarpThreads, 0) != cudaSuccess) return 0;
     if (occ < 1) occ = 1;
     *cache = sms * occ;
     return *cache;
 }
 
+constexpr int kCtaSlotsExtra = 1024;   // the workspace holds n_maps + kCtaSlotsExtra per-CTA slots (lh_heatmap_ws_bytes)
+constexpr int kMaxPieces = 16;
+
 template <bool PRED, int TSRC, int FLAGS>
-static int launch_vec(const HeatmapParams& p, cudaStream_t st) {
+static int launch_vec(const HeatmapParams& p0, cudaStream_t st) {
     static int cache = 0;   // one device model per process (B200); benign race: same value
-    const int cap = persistent_grid(heatmap_vec_kernel<PRED, TSRC, FLAGS>, &cache);
+    const int cap = persistent_grid(heatmap_warp_kernel<PRED, TSRC, FLAGS>, &cache);
     if (cap <= 0) return (int)cudaGetLastError();
-    const unsigned grid = (unsigned)(p.n_maps < (long long)cap ? p.n_maps : (long long)cap);
-    heatmap_vec_kernel<PRED, TSRC, FLAGS><<<grid, kVecThreads, 0, st>>>(p);
+    HeatmapParams p = p0;
+    const int V = p.HW >> 2;
+    p.WR = (V + 31) / 32;
+    p.vinv = ((1u << 20) + (unsigned)(p.W >> 2) - 1u) / (unsigned)(p.W >> 2);
+    // work list: whole maps first, the remainder cut into pieces so that the last round fills the machine
+    long long grid = p.n_maps * (long long)kMaxPieces;        // warps that could be given work at all ...
+    grid = (grid + kWarpsPerCta - 1) / kWarpsPerCta;          // ... as CTAs
+    if (grid > cap) grid = cap;
+    if (grid > p.n_maps + kCtaSlotsExtra) grid = p.n_maps + kCtaSlotsExtra;   // per-CTA slots in the workspace
+    if (grid < 1) grid = 1;
+    const long long Wt = grid * kWarpsPerCta;
+    p.n_full = (p.n_maps / Wt) * Wt;
+    const long long rem = p.n_maps - p.n_full;
+    constexpr bool kDecode = PRED && (FLAGS & F_DEC) != 0;
+    long long P = 1;
+    if (rem > 0 && (!kDecode || p.map_key != nullptr)) {      // pieces of a decoded map meet in the workspace
+        P = Wt / rem;
+        if (P > kMaxPieces) P = kMaxPieces;
+        if (P > p.WR) P = p.WR;
+        if (P < 1) P = 1;
+    }
+    p.P = (int)P;
+    p.units = p.n_full + rem * P;
+    if (p.units >= (1LL << 31)) return LH_EUNSUPPORTED;
+    const long long need = (p.units + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (grid > need) grid = need;
+    // NOTE: n_full / P were derived from Wt of the capped grid; a smaller final grid only changes who takes which unit
+    heatmap_warp_kernel<PRED, TSRC, FLAGS><<<(unsigned)grid, kWarpThreads, 0, st>>>(p);
     return LH_OK;
 }
 
@@ -691,7 +730,8 @@ static int launch(HeatmapParams& p, bool vec, cudaStream_t st) {
 }
 
 static bool can_vec(const HeatmapParams& p) {
-    if ((p.W & 3) != 0 || (p.W >> 2) > kVecThreads) return false;
+    // float4 rows; (v * vinv) >> 20 == v / (W/4) needs v * (W/4) < 2^20 for every vector index v < H*W/4
+    if ((p.W & 3) != 0 || (long long)(p.HW >> 2) * (p.W >> 2) >= (1 << 20)) return false;
     const void* ptrs[] = {p.pred, p.target_in, p.target_out, p.grad};
     for (const void* q : ptrs) if (q && !aligned16(q)) return false;
     return true;
@@ -706,10 +746,13 @@ static int check_geom(long long N, int J, int H, int W) {
 static void fill_ws(HeatmapParams& p, void* ws) {
     char* b = reinterpret_cast<char*>(ws);
     p.ticket = reinterpret_cast<unsigned int*>(b);
-    // one slot per CTA; the grid never exceeds n_maps
+    // one slot per CTA: the grid never exceeds n_maps + kCtaSlotsExtra
+    const size_t slots = (size_t)p.n_maps + kCtaSlotsExtra;
     p.cta_loss = reinterpret_cast<double*>(b + 16);
-    p.cta_epe = reinterpret_cast<double*>(b + 16 + 8 * (size_t)p.n_maps);
-    p.cta_wrong = reinterpret_cast<unsigned int*>(b + 16 + 16 * (size_t)p.n_maps);
+    p.cta_epe = reinterpret_cast<double*>(b + 16 + 8 * slots);
+    p.cta_wrong = reinterpret_cast<unsigned int*>(b + 16 + 16 * slots);
+    p.map_key = reinterpret_cast<unsigned long long*>(b + 16 + 24 * slots);
+    p.map_cnt = reinterpret_cast<unsigned int*>(b + 16 + 24 * slots + 8 * (size_t)p.n_maps);
 }
 
 }  // namespace lh
@@ -718,7 +761,9 @@ using namespace lh;
 
 extern "C" size_t lh_heatmap_ws_bytes(int64_t N, int J) {
     if (N < 0 || J < 0) return 0;
-    return 16 + 24 * (size_t)N * (size_t)J;
+    const size_t maps = (size_t)N * (size_t)J;
+    // ticket | per-CTA slots (loss f64, epe f64, wrong u32) | per-map combine words of split maps (key u64, count u32)
+    return 16 + 24 * (maps + kCtaSlotsExtra) + 16 * maps;
 }
 
 extern "C" int lh_gen_targets(const float* joints, int joint_stride, int N, int J, int H, int W,

@@ -50,6 +50,34 @@ __device__ __forceinline__ uint32_t order_key(float v) {
 }
 
 
+// ---- mbarrier / bulk-copy (TMA) primitives shared by the K1 ring (warp_tma.cu) and the heat-map ring (heatmap.cu) ------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+// try_wait parks the warp in hardware until the phase completes or the hint (ns) runs out: few spin instructions
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "LH_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra LH_DONE;\n\t"
+        "bra LH_WAIT;\n\t"
+        "LH_DONE:\n\t}"
+        :: "r"(bar), "r"(parity), "r"(20000u) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared (TMA engine), completion counted in bytes on `bar`; 16-byte aligned, size % 16 == 0
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 // ---- cv2.warpAffine coordinate arithmetic, shared by the warp kernels -----------------
 __device__ __forceinline__ int clamp_i(int v, int lo, int hi) { return min(max(v, lo), hi); }
 

@@ -43,27 +43,6 @@ struct __align__(16) StageInfo { int lox, hix, loy, hiy, flags, n, tx0, ty0, bas
 constexpr int kStageBytes2 = ((kRawBytes + 4 * 32 * 4 + (int)sizeof(StageInfo)) + 127) & ~127;   // 8320
 static_assert(kRawBytes % 128 == 0, "TMA destinations must stay 128-byte aligned");
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-// try_wait parks the warp in hardware until the phase completes or the hint (ns) runs out: few spin instructions
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "LH_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-        "@p bra LH_DONE;\n\t"
-        "bra LH_WAIT;\n\t"
-        "LH_DONE:\n\t}"
-        :: "r"(bar), "r"(parity), "r"(20000u) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"

@@ -29,7 +29,7 @@ def test_version_and_error_text():
     assert lib.lh_abi_version() == _lib.ABI_VERSION == 4
     assert b"NULL" in lib.lh_strerror(-2)
     assert lib.lh_strerror(-1).startswith(b"lighthand_b200")
-    assert lib.lh_heatmap_ws_bytes(256, 21) == 16 + 24 * 256 * 21
+    assert lib.lh_heatmap_ws_bytes(256, 21) == 16 + 24 * (256 * 21 + 1024) + 16 * 256 * 21
 
 
 def test_argument_validation_needs_no_device():
