@@ -89,12 +89,17 @@ int lh_warp_normalize(const uint8_t* src,        /* dev N HWC RGB uint8 images  
  * gauss_table: dev side*side float32, computed by the caller exactly as the reference does with
  * numpy (bit-exact targets).  style 0: side = 2*tmp+1.  style 1: side = 6*sigma+3, sigma = H/64 integer.
  * target_weight dev [N,J] or NULL.
+ * use_vis = 0: the reference's behaviour -- target_weight = 1 where the Gaussian window meets the map, else 0
+ * (computed and discarded at src/tools/dataset.py:171,185,212; visibility never consulted).
+ * use_vis = 1 (joint_stride >= 3): upstream-HRNet semantics the north star names -- target_weight = visibility
+ * (third joint column) * in-bounds, and the Gaussian is drawn only where that is > 0.5 (oracle.restate.generate_target
+ * use_vis=True; parity unpinned: not in the reference).
  * ------------------------------------------------------------------------------------------ */
 #define LH_TARGET_HRNET     0
 #define LH_TARGET_HOURGLASS 1
 int lh_gen_targets(const float* joints, int joint_stride /*floats per joint: 2 or 3*/,
                    int N, int J, int H, int W, float stride_x, float stride_y,
-                   int style, const float* gauss_table, int table_side,
+                   int style, int use_vis, const float* gauss_table, int table_side,
                    float* target, float* target_weight, lh_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -160,6 +165,7 @@ typedef struct lh_heatmap_args {
     float out_scale;
     float pck_thr;              /* threshold as float32: T ('proportion') or T*3.78 ('mm') */
     int32_t pck_mode;           /* LH_PCK_*                                                */
+    int32_t use_vis;            /* 1: target_weight = visibility * in-bounds (see lh_gen_targets) */
 } lh_heatmap_args;
 int lh_heatmap_fused(const lh_heatmap_args* args, lh_stream_t stream);
 
@@ -192,6 +198,25 @@ int lh_pck_curve_accum(const float* pred_xy, const float* gt, int gt_stride,
                        int64_t N, int J, const double* thr_sorted, int K, int method, int use_vis,
                        unsigned long long* hist, unsigned long long* n_valid,
                        unsigned long long* n_all, double* sum_d, lh_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched keypoint transform.  Replaces the keypoint half of augmentation()  src/utils/preprocessing.py:83-90:
+ *   if flipped: x = orig_w - x - 1 (float32), left / right joints (and their validity) swapped;
+ *   (x, y) = trans_point2d((x, y), trans) = float64 dot of the float32 2x3 crop matrix with (x, y, 1)
+ *            (src/utils/preprocessing.py:207-210), stored back as float32;
+ *   joint_valid *= (0 <= x < out_w) * (0 <= y < out_h).
+ * joints dev [N,J,joint_stride] (x, y[, visibility]); valid_in dev [N,J] or NULL (then the visibility column when
+ * joint_stride >= 3, else 1); trans dev [N,2,3] double holding the float32 matrix values; flip dev [N] or NULL;
+ * swap dev int32 [J] or NULL: swap[j] = the joint whose data slot j receives on a flip (an involution; identity
+ * for a single hand).  joints_out dev [N,J,out_stride] (x, y[, valid]); valid_out dev [N,J] or NULL.
+ * ------------------------------------------------------------------------------------------ */
+int lh_transform_joints(const float* joints, int joint_stride, const float* valid_in, const double* trans,
+                        const uint8_t* flip, int orig_w, const int32_t* swap, int64_t N, int J, int out_w, int out_h,
+                        float* joints_out, int out_stride, float* valid_out, lh_stream_t stream);
+
+/* bounding-box diagonal of the ground-truth joints of each sample, float32, exactly as the per-sample Python loops do it
+ * (builtin max / min; src/utils/argparser.py:268-272, src/utils/loss.py:122-127).  gt dev [N,J,gt_stride] -> out dev [N]. */
+int lh_bbox_diag(const float* gt, int gt_stride, int64_t N, int J, float* out, lh_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K6  metric all-reduce: the path's only collective.  The batch is data-partitioned, one

@@ -39,7 +39,7 @@ class HeatmapArgs(C.Structure):
         ("N", c_i64), ("J", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("joint_stride", C.c_int32),
         ("table_side", C.c_int32), ("style", C.c_int32), ("use_target_weight", C.c_int32),
         ("subpixel", C.c_int32), ("stride_x", c_f), ("stride_y", c_f), ("out_scale", c_f), ("pck_thr", c_f),
-        ("pck_mode", C.c_int32),
+        ("pck_mode", C.c_int32), ("use_vis", C.c_int32),
     ]
 
 
@@ -81,7 +81,9 @@ PROTOTYPES = {
     "lh_norm_lut_build": (c_i, [c_p, c_i, c_p, c_p, c_p]),
     "lh_warp_normalize": (c_i, [c_p, c_i64, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p,
                                 c_i, c_i, c_i, c_p]),
-    "lh_gen_targets": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_i, c_p, c_i, c_p, c_p, c_p]),
+    "lh_gen_targets": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_i, c_i, c_p, c_i, c_p, c_p, c_p]),
+    "lh_transform_joints": (c_i, [c_p, c_i, c_p, c_p, c_p, c_i, c_p, c_i64, c_i, c_i, c_i, c_p, c_i, c_p, c_p]),
+    "lh_bbox_diag": (c_i, [c_p, c_i, c_i64, c_i, c_p, c_p]),
     "lh_heatmap_ws_bytes": (C.c_size_t, [c_i64, c_i]),
     "lh_jmse_loss": (c_i, [c_p, c_p, c_p, c_i64, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
     "lh_decode": (c_i, [c_p, c_i64, c_i, c_i, c_i, c_f, c_i, c_p, c_p, c_p, c_p, c_p]),

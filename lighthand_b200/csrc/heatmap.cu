@@ -58,6 +58,7 @@ struct HeatmapParams {
     long long n_maps;
     int J, H, W, HW;
     int joint_stride, side, style, use_weight, subpixel;
+    int use_vis;                // upstream HRNet: target_weight = visibility (3rd joint column) * in-bounds, drawn when > 0.5
     int pck_mode;
     float pck_thr;
     float stride_x, stride_y, out_scale;
@@ -358,9 +359,12 @@ __global__ void __launch_bounds__(kWarpThreads, TSRC == 2 ? 3 : LH_HM_MINB) heat
         // ---- per-map setup: ONE coalesced load brings the sample's J ground-truth joints (lane = joint); the map's own
         // joint (window, PCK / EPE record) and the first joint (bbox quirk) come out of it by shuffle ----------------
         float2 jl = make_float2(0.f, 0.f), gj = jl, jfirst = jl;
+        float vis = 1.0f;                                        // the map's joint visibility (use_vis only)
         const bool need_j = (TSRC == 1) || do_metric;
         if (need_j) {
             const int jm = m % p.J;
+            const float* jp = p.joints + (long long)m * p.joint_stride;
+            if (TSRC == 1 && p.use_vis) vis = jp[2];
             if (p.J <= 32) {
                 if (lane < p.J) {
                     const float* gp = p.joints + ((long long)(m - jm) + lane) * p.joint_stride;
@@ -369,7 +373,6 @@ __global__ void __launch_bounds__(kWarpThreads, TSRC == 2 ? 3 : LH_HM_MINB) heat
                 gj = make_float2(__shfl_sync(0xffffffffu, jl.x, jm), __shfl_sync(0xffffffffu, jl.y, jm));
                 jfirst = make_float2(__shfl_sync(0xffffffffu, jl.x, 0), __shfl_sync(0xffffffffu, jl.y, 0));
             } else {
-                const float* jp = p.joints + (long long)m * p.joint_stride;
                 const float* gp = p.joints + (long long)(m - jm) * p.joint_stride;
                 gj = make_float2(jp[0], jp[1]);
                 jfirst = make_float2(gp[0], gp[1]);
@@ -379,10 +382,13 @@ __global__ void __launch_bounds__(kWarpThreads, TSRC == 2 ? 3 : LH_HM_MINB) heat
         float wgt = 1.0f, gs = p.grad_scale;
         if (TSRC == 1) {
             const Window win = joint_window(p, gj.x, gj.y);
-            const bool valid = win.valid != 0;
+            // reference: target_weight = in-bounds (computed, then discarded).  use_vis (upstream HRNet semantics the
+            // north star names): target_weight = visibility * in-bounds, and the Gaussian is drawn only when it is > 0.5
+            const float tw = win.valid ? vis : 0.0f;
+            const bool valid = p.use_vis ? (tw > 0.5f) : (win.valid != 0);
             if (valid) { ulx = win.ulx; uly = win.uly; wwin = win.brx - win.ulx; hwin = win.bry - win.uly; }
-            if (p.weight_out && lane == 0 && k == 0) p.weight_out[m] = valid ? 1.0f : 0.0f;
-            if (WGT && !p.weight_in) wgt = valid ? 1.0f : 0.0f;
+            if (p.weight_out && lane == 0 && k == 0) p.weight_out[m] = tw;
+            if (WGT && !p.weight_in) wgt = tw;
         }
         if (WGT) {
             if (p.weight_in) wgt = p.weight_in[m];
@@ -531,6 +537,7 @@ __global__ void __launch_bounds__(kThreads) heatmap_scalar_kernel(const HeatmapP
 
     Window win;
     win.valid = 0; win.ulx = win.uly = win.brx = win.bry = 0;
+    float tw = 0.0f;            // target weight of this map (TSRC == 1)
     float2 gj = make_float2(0.f, 0.f), jl = gj, jfirst = gj;
     const bool do_loss = PRED && TSRC != 0;
     const bool do_dec = PRED && p.coords != nullptr;
@@ -542,6 +549,8 @@ __global__ void __launch_bounds__(kThreads) heatmap_scalar_kernel(const HeatmapP
     if (TSRC == 1) {
         for (int i = tid; i < p.side * p.side; i += kThreads) s_tab[i] = p.table[i];
         win = joint_window(p, gj.x, gj.y);
+        tw = win.valid ? (p.use_vis ? p.joints[m * p.joint_stride + 2] : 1.0f) : 0.0f;
+        if (p.use_vis && !(tw > 0.5f)) win.valid = 0;
         if (!win.valid) { win.ulx = win.uly = 0; win.brx = win.bry = 0; }
         __syncthreads();
     }
@@ -553,9 +562,9 @@ __global__ void __launch_bounds__(kThreads) heatmap_scalar_kernel(const HeatmapP
     float wgt = 1.0f;
     if (p.use_weight) {
         if (p.weight_in) wgt = p.weight_in[m];
-        else if (TSRC == 1) wgt = win.valid ? 1.0f : 0.0f;
+        else if (TSRC == 1) wgt = tw;
     }
-    if (TSRC == 1 && p.weight_out && tid == 0) p.weight_out[m] = win.valid ? 1.0f : 0.0f;
+    if (TSRC == 1 && p.weight_out && tid == 0) p.weight_out[m] = tw;
 
     const size_t base = (size_t)m * p.HW;
     const float* pred = PRED ? p.pred + base : nullptr;
@@ -767,18 +776,19 @@ extern "C" size_t lh_heatmap_ws_bytes(int64_t N, int J) {
 }
 
 extern "C" int lh_gen_targets(const float* joints, int joint_stride, int N, int J, int H, int W,
-                              float stride_x, float stride_y, int style, const float* gauss_table,
+                              float stride_x, float stride_y, int style, int use_vis, const float* gauss_table,
                               int table_side, float* target, float* target_weight, lh_stream_t stream) {
     if (!joints || !gauss_table || !target) return LH_ENULL;
     int rc = check_geom(N, J, H, W);
     if (rc) return rc;
     if (joint_stride < 2 || table_side < 1 || (table_side & 1) == 0 || table_side * table_side > kMaxTable) return LH_EINVAL;
+    if (use_vis && joint_stride < 3) return LH_EINVAL;           // visibility = third joint column
     if (style != LH_TARGET_HRNET && style != LH_TARGET_HOURGLASS) return LH_EINVAL;
     if (!(stride_x > 0.f) || !(stride_y > 0.f)) return LH_EINVAL;
     HeatmapParams p{};
     p.joints = joints; p.table = gauss_table; p.target_out = target; p.weight_out = target_weight;
     p.n_maps = (long long)N * J; p.J = J; p.H = H; p.W = W; p.HW = H * W;
-    p.joint_stride = joint_stride; p.side = table_side; p.style = style;
+    p.joint_stride = joint_stride; p.side = table_side; p.style = style; p.use_vis = use_vis != 0;
     p.stride_x = stride_x; p.stride_y = stride_y;
     return launch<false, 1>(p, can_vec(p), (cudaStream_t)stream);
 }
@@ -824,7 +834,7 @@ extern "C" int lh_heatmap_fused(const lh_heatmap_args* a, lh_stream_t stream) {
     p.coords = a->coords; p.maxvals = a->maxvals; p.argidx = a->argidx;
     p.n_maps = (long long)a->N * a->J; p.J = a->J; p.H = a->H; p.W = a->W; p.HW = a->H * a->W;
     p.joint_stride = a->joint_stride; p.side = a->table_side; p.style = a->style;
-    p.use_weight = a->use_target_weight; p.subpixel = a->subpixel;
+    p.use_weight = a->use_target_weight; p.subpixel = a->subpixel; p.use_vis = a->use_vis != 0;
     p.stride_x = a->stride_x; p.stride_y = a->stride_y; p.out_scale = a->out_scale;
     if (a->metric_counts || a->metric_sums) {
         // fused K5 needs the decode, the ground-truth joints and both accumulators
@@ -843,6 +853,7 @@ extern "C" int lh_heatmap_fused(const lh_heatmap_args* a, lh_stream_t stream) {
     }
     if (a->joint_stride < 2 || a->table_side < 1 || (a->table_side & 1) == 0 ||
         a->table_side * a->table_side > kMaxTable) return LH_EINVAL;
+    if (a->use_vis && a->joint_stride < 3) return LH_EINVAL;
     if (!(a->stride_x > 0.f) || !(a->stride_y > 0.f)) return LH_EINVAL;
     return launch<true, 1>(p, can_vec(p), (cudaStream_t)stream);
 }

@@ -165,9 +165,65 @@ pck_curve_kernel(const float* __restrict__ pred, const float* __restrict__ gt, i
         if (s_hist[i]) atomicAdd(hist + i, (unsigned long long)s_hist[i]);
 }
 
+
+// one thread per (sample, joint)
+__global__ void transform_joints_kernel(const float* __restrict__ joints, int js, const float* __restrict__ valid_in,
+                                        const double* __restrict__ trans, const uint8_t* __restrict__ flip, int orig_w,
+                                        const int32_t* __restrict__ swap, long long total, int J, int out_w, int out_h,
+                                        float* __restrict__ out, int os, float* __restrict__ valid_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long n = i / J;
+    const int j = (int)(i - n * J);
+    const bool f = flip ? (flip[n] != 0) : false;
+    const int sj = (f && swap) ? swap[j] : j;                     // slot j receives joint sj's data on a flip
+    const float* g = joints + (n * J + sj) * js;
+    float x = g[0];
+    const float y = g[1];
+    float v = valid_in ? valid_in[n * J + sj] : (js >= 3 ? g[2] : 1.0f);
+    if (f) x = __fsub_rn(__fsub_rn((float)orig_w, x), 1.0f);      // float32, like numpy on a float32 array
+    const double* t = trans + n * 6;
+    // np.dot(trans, [x, y, 1.]) in float64, left to right; stored into the float32 joint array
+    const double dx = __dadd_rn(__dadd_rn(__dmul_rn(t[0], (double)x), __dmul_rn(t[1], (double)y)), t[2]);
+    const double dy = __dadd_rn(__dadd_rn(__dmul_rn(t[3], (double)x), __dmul_rn(t[4], (double)y)), t[5]);
+    const float ox = (float)dx, oy = (float)dy;
+    v = v * (float)(ox >= 0.f) * (float)(ox < (float)out_w) * (float)(oy >= 0.f) * (float)(oy < (float)out_h);
+    float* o = out + i * os;
+    o[0] = ox; o[1] = oy;
+    if (os >= 3) o[2] = v;
+    if (valid_out) valid_out[i] = v;
+}
+
+__global__ void bbox_diag_kernel(const float* __restrict__ gt, int gs, long long N, int J, float* __restrict__ out) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < N) out[n] = bbox_diag_f32(gt + n * J * gs, J, gs);
+}
+
 }  // namespace lh
 
 using namespace lh;
+
+extern "C" int lh_transform_joints(const float* joints, int joint_stride, const float* valid_in, const double* trans,
+                                   const uint8_t* flip, int orig_w, const int32_t* swap, int64_t N, int J, int out_w,
+                                   int out_h, float* joints_out, int out_stride, float* valid_out, lh_stream_t stream) {
+    if (!joints || !trans || !joints_out) return LH_ENULL;
+    if (N < 0 || J <= 0 || joint_stride < 2 || out_stride < 2 || out_w <= 0 || out_h <= 0) return LH_EINVAL;
+    if (N == 0) return LH_OK;
+    const long long total = (long long)N * J;
+    transform_joints_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        joints, joint_stride, valid_in, trans, flip, orig_w, swap, total, J, out_w, out_h, joints_out, out_stride, valid_out);
+    LH_CHECK_LAUNCH();
+    return LH_OK;
+}
+
+extern "C" int lh_bbox_diag(const float* gt, int gt_stride, int64_t N, int J, float* out, lh_stream_t stream) {
+    if (!gt || !out) return LH_ENULL;
+    if (N < 0 || J <= 0 || gt_stride < 2) return LH_EINVAL;
+    if (N == 0) return LH_OK;
+    bbox_diag_kernel<<<(unsigned)((N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(gt, gt_stride, (long long)N, J, out);
+    LH_CHECK_LAUNCH();
+    return LH_OK;
+}
 
 extern "C" int lh_pck_epe_batch(const float* pred_xy, const float* gt, int gt_stride, int64_t N, int J,
                                 float thr_f32, int mode, int visible, unsigned long long* counts,

@@ -259,8 +259,10 @@ def color_jitter_normalize(images: torch.Tensor, params, mean=IMAGENET_MEAN, std
 
 def gen_targets(joints: torch.Tensor, heatmap_hw=(64, 64), feat_stride=(4.0, 4.0), sigma: float = 2,
                 style: int = LH_TARGET_HRNET, want_weight: bool = True,
-                out: Optional[torch.Tensor] = None):
-    """K2.  joints [N,J,2|3] float32 CUDA (network-input pixels) -> (target [N,J,H,W], weight [N,J,1])."""
+                out: Optional[torch.Tensor] = None, use_vis: bool = False):
+    """K2.  joints [N,J,2|3] float32 CUDA (network-input pixels) -> (target [N,J,H,W], weight [N,J,1]).
+    ``use_vis``: target_weight = visibility (third column) * in-bounds and joints with weight <= 0.5 get an empty map
+    (upstream HRNet; the reference ignores visibility -- the default)."""
     require_cuda()
     lib = _lib.load()
     joints = _dev(joints, torch.float32, "joints")
@@ -281,7 +283,7 @@ def gen_targets(joints: torch.Tensor, heatmap_hw=(64, 64), feat_stride=(4.0, 4.0
         return out, weight
     with torch.cuda.device(joints.device):
         check(lib.lh_gen_targets(joints.data_ptr(), js, n, j, h, w, float(feat_stride[0]), float(feat_stride[1]),
-                                 style, table.data_ptr(), side, out.data_ptr(), _ptr(weight), _stream()),
+                                 style, int(bool(use_vis)), table.data_ptr(), side, out.data_ptr(), _ptr(weight), _stream()),
               "lh_gen_targets")
     return out, weight
 
@@ -303,6 +305,41 @@ def heatmap_workspace(n: int, j: int, device) -> torch.Tensor:
         ws = torch.zeros((nbytes + 7) // 8, dtype=torch.int64, device=device)
         _ws_cache[key] = ws
     return ws
+
+
+def transform_joints(joints: torch.Tensor, trans: torch.Tensor, out_hw, flip: Optional[torch.Tensor] = None,
+                     orig_w: int = 0, swap: Optional[torch.Tensor] = None, valid: Optional[torch.Tensor] = None):
+    """Keypoint half of ``augmentation`` (src/utils/preprocessing.py:83-90), batched on the device: mirror + left/right
+    swap for flipped samples, ``trans_point2d`` with the crop matrix, ``joint_valid`` in-image test.
+    joints [N,J,2|3] float32; trans [N,2,3] (the float32 matrices ``generate_patch_image`` returns, any float dtype);
+    returns (joints_out [N,J,3] = x, y, valid; valid [N,J])."""
+    require_cuda()
+    lib = _lib.load()
+    joints = _dev(joints, torch.float32, "joints")
+    n, j, js = joints.shape
+    trans = _dev(trans.to(torch.float64) if trans.dtype != torch.float64 else trans, torch.float64, "trans")
+    flip = _dev(flip, torch.uint8, "flip") if flip is not None else None
+    swap = _dev(swap, torch.int32, "swap") if swap is not None else None
+    valid = _dev(valid, torch.float32, "valid").reshape(n, j) if valid is not None else None
+    out = torch.empty((n, j, 3), dtype=torch.float32, device=joints.device)
+    vout = torch.empty((n, j), dtype=torch.float32, device=joints.device)
+    with torch.cuda.device(joints.device):
+        check(lib.lh_transform_joints(joints.data_ptr(), js, _ptr(valid), trans.data_ptr(), _ptr(flip), int(orig_w),
+                                      _ptr(swap), n, j, int(out_hw[1]), int(out_hw[0]), out.data_ptr(), 3,
+                                      vout.data_ptr(), _stream()), "lh_transform_joints")
+    return out, vout
+
+
+def bbox_diag(gt: torch.Tensor) -> torch.Tensor:
+    """float32 bounding-box diagonal of each sample's joints [N,J,>=2] -> [N] (src/utils/argparser.py:268-272)."""
+    require_cuda()
+    lib = _lib.load()
+    gt = _dev(gt, torch.float32, "gt")
+    n, j, gs = gt.shape
+    out = torch.empty((n,), dtype=torch.float32, device=gt.device)
+    with torch.cuda.device(gt.device):
+        check(lib.lh_bbox_diag(gt.data_ptr(), gs, n, j, out.data_ptr(), _stream()), "lh_bbox_diag")
+    return out
 
 
 def jmse_loss(pred: torch.Tensor, target: torch.Tensor, weight: Optional[torch.Tensor] = None,
@@ -355,7 +392,7 @@ def heatmap_fused(pred: torch.Tensor, joints: Optional[torch.Tensor] = None, *,
                   inv_affine: Optional[torch.Tensor] = None, use_target_weight: bool = False,
                   loss_meter: Optional[torch.Tensor] = None, buffers: Optional[dict] = None,
                   metrics: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, pck_T: float = 0.2,
-                  pck_threshold: str = "proportion") -> dict:
+                  pck_threshold: str = "proportion", use_vis: bool = False) -> dict:
     """Fused K2+K3+K4: one read of ``pred`` gives loss, grad, target (optional) and decode.
     ``buffers`` may carry preallocated outputs (keys: target, grad, loss, coords, maxvals, argidx, weight)
     so the call is allocation-free (CUDA-graph capturable).  ``metrics=(counts, sums)`` (see
@@ -412,6 +449,7 @@ def heatmap_fused(pred: torch.Tensor, joints: Optional[torch.Tensor] = None, *,
     a.N, a.J, a.H, a.W = n, j, h, w
     a.style = style
     a.use_target_weight = int(bool(use_target_weight))
+    a.use_vis = int(bool(use_vis))
     a.subpixel = int(bool(subpixel))
     a.stride_x, a.stride_y = float(feat_stride[0]), float(feat_stride[1])
     a.out_scale = float(out_scale)

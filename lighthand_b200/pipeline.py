@@ -33,9 +33,10 @@ class HeatmapPipeline:
                  sigma: float = 2, interp: int = ops.LH_INTERP_CV2_U8, train: bool = True,
                  materialize_target: bool = False, subpixel: bool = False, map_back: bool = False,
                  pck_T: float = 0.2, mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD, device="cuda",
-                 use_graph: bool = False, exact_norm: bool = False):
+                 use_graph: bool = False, exact_norm: bool = False, use_vis: bool = False):
         ops.require_cuda()
         self.exact_norm = exact_norm
+        self.use_vis = use_vis          # target_weight = visibility * in-bounds (joints [N,J,3]); default: the reference's
         self.device = torch.device(device)
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
@@ -83,7 +84,7 @@ class HeatmapPipeline:
                           out_scale=self.stride[0], subpixel=self.subpixel,
                           inv_affine=inv_affine if self.map_back else None,
                           loss_meter=self.meter.loss_meter, buffers=self.buffers,
-                          metrics=(self.meter.counts, self.meter.sums), pck_T=self.pck_T)
+                          metrics=(self.meter.counts, self.meter.sums), pck_T=self.pck_T, use_vis=self.use_vis)
 
     def step(self, images_u8: torch.Tensor, fwd_affine: Optional[torch.Tensor], joints: torch.Tensor,
              pred: torch.Tensor, flip: Optional[torch.Tensor] = None, inv_affine: Optional[torch.Tensor] = None) -> dict:
@@ -182,7 +183,7 @@ class HeatmapPipeline:
                           out_scale=self.stride[0], subpixel=self.subpixel,
                           inv_affine=inv_affine if self.map_back else None,
                           loss_meter=self.meter.loss_meter, buffers=self.buffers,
-                          metrics=(self.meter.counts, self.meter.sums), pck_T=self.pck_T)
+                          metrics=(self.meter.counts, self.meter.sums), pck_T=self.pck_T, use_vis=self.use_vis)
         self._loss_end()
         out = dict(self.buffers)
         out["input"] = inp
@@ -271,6 +272,7 @@ class PreparedStep:
         a.ws = b["ws"].data_ptr()
         a.N, a.J, a.H, a.W = p.N, p.J, p.hm_hw[0], p.hm_hw[1]
         a.style, a.use_target_weight, a.subpixel = ops.LH_TARGET_HRNET, 0, int(bool(p.subpixel))
+        a.use_vis = int(bool(p.use_vis))
         a.stride_x, a.stride_y, a.out_scale = float(p.stride[0]), float(p.stride[1]), float(p.stride[0])
         self._args = a
         a.metric_counts, a.metric_sums = p.meter.counts.data_ptr(), p.meter.sums.data_ptr()

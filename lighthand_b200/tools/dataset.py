@@ -69,15 +69,34 @@ class GpuCollate:
     S / S_src (src/tools/dataset.py:132).  A dataset that yields a third element per sample,
     ``(image, joint_2d, augment)``, gets ``ColorJitter(0.5, 0.5, 0.5, 0.5)`` on the samples whose flag is true
     (the reference's ``idx < len(meta) * ratio_of_aug``, src/tools/dataset.py:134-146), drawn per sample from
-    torch's generator in torchvision's order."""
+    torch's generator in torchvision's order.  ``phase="eval"``: the Armo evaluation set's item shape, see ``_eval_batch``."""
 
     def __init__(self, image_size=256, heatmap_size=64, sigma=2, device="cuda",
-                 mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD, jitter=(0.5, 0.5, 0.5, 0.5)):
+                 mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD, jitter=(0.5, 0.5, 0.5, 0.5), phase="train"):
         self.image_size, self.heatmap_size, self.sigma = image_size, heatmap_size, sigma
         self.device, self.mean, self.std = torch.device(device), mean, std
         self.jitter = jitter
+        self.phase = phase
+
+    def _eval_batch(self, samples):
+        """``eval_set.__getitem__`` with ``phase == "eval"`` (src/tools/dataset.py:257-300) + default collate: samples are
+        ``(image_u8_hwc, joint [21, >=2] normalised to 0..1, visible [21], pose_type, idx)``; returns what ``pred_store``
+        iterates over (src/utils/argparser.py:255-257): ``(images f32[N,3,S,S], joint_2d_v f32[N,21,3] = x*S, y*S, vis,
+        [pose_types, idx])``.  ToTensor -> Resize -> Normalize runs batched on the device."""
+        imgs = np.stack([np.asarray(s[0], dtype=np.uint8) for s in samples])
+        joint = torch.stack([torch.as_tensor(s[1], dtype=torch.float32)[:, :2] for s in samples])
+        vis = torch.stack([torch.as_tensor(s[2], dtype=torch.float32) for s in samples])
+        joint_2d_v = torch.cat([joint * self.image_size, vis[:, :, None]], dim=2)      # :286-289
+        d_imgs = torch.from_numpy(imgs).to(self.device, non_blocking=True)
+        images = ops.warp_normalize(d_imgs, None, (self.image_size, self.image_size), mean=self.mean, std=self.std,
+                                    interp=ops.LH_INTERP_TORCH)
+        pose = [s[3] for s in samples]
+        idx = [s[4] for s in samples]
+        return images, joint_2d_v.to(self.device, non_blocking=True), [pose, idx]
 
     def __call__(self, samples):
+        if self.phase == "eval":
+            return self._eval_batch(samples)
         imgs = np.stack([np.asarray(s[0], dtype=np.uint8) for s in samples])
         joints = torch.stack([torch.as_tensor(s[1], dtype=torch.float32)[:, :2] for s in samples])
         src = imgs.shape[1]

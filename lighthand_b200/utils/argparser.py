@@ -104,27 +104,33 @@ def pred_store(args, dataloader, model, pbar):
     category and write ``output/<args.name>/evaluation.json`` in the reference's schema
     ``[{category: {"bb": [n], "pred": [n][21][2], "gt": [n][21][3]}}]``.
 
-    The decode and the bounding-box diagonals are computed on the device (``ops.decode``; float32
-    max/min/sqrt like the reference's per-sample loop); one device->host copy per batch feeds the JSON lists.
+    The decode and the bounding-box diagonals are computed on the device (``lh_decode``, ``lh_bbox_diag``: float32
+    builtin max / min / sqrt exactly like the reference's per-sample loop); results stay on the device for the whole
+    sweep and ONE device->host copy at the end feeds the JSON lists.
     Returns the meta dict as well."""
     from .dir import dump
     meta = {name: {"bb": [], "pred": [], "gt": []} for name in POSE_CATEGORIES}
     dev = next(model.parameters()).device
+    coords_all, bbox_all, gt_all, anno_all = [], [], [], []
     with torch.no_grad():
         for images, gt_2d_joints, annos in dataloader:
             anno, _idx = annos
             pred = model(images.to(dev, non_blocking=True))
             coords, _mv, _ai = ops.decode(pred.float().contiguous(), 4.0)
             gt = gt_2d_joints.to(dev, torch.float32)
-            width = gt[:, :, 0].amax(1) - gt[:, :, 0].amin(1)
-            height = gt[:, :, 1].amax(1) - gt[:, :, 1].amin(1)
-            bbox = torch.sqrt(width * width + height * height)
-            pred_l, bbox_l, gt_l = coords.cpu().tolist(), bbox.cpu().tolist(), gt_2d_joints.tolist()
-            for i, name in enumerate(anno):
-                meta[name]["bb"].append(bbox_l[i])
-                meta[name]["pred"].append(pred_l[i])
-                meta[name]["gt"].append(gt_l[i])
+            coords_all.append(coords)
+            bbox_all.append(ops.bbox_diag(gt))                 # lh_bbox_diag: the per-sample loop of :268-272, float32
+            gt_all.append(gt_2d_joints)
+            anno_all.extend(anno)
             pbar.update(1)
+    if coords_all:
+        # ONE device->host copy for the whole sweep, then the reference's bucketing into JSON lists
+        pred_l, bbox_l = torch.cat(coords_all).cpu().tolist(), torch.cat(bbox_all).cpu().tolist()
+        gt_l = torch.cat([g.cpu() if isinstance(g, torch.Tensor) else torch.as_tensor(g) for g in gt_all]).tolist()
+        for i, name in enumerate(anno_all):
+            meta[name]["bb"].append(bbox_l[i])
+            meta[name]["pred"].append(pred_l[i])
+            meta[name]["gt"].append(gt_l[i])
     os.makedirs(os.path.join("output", args.name), exist_ok=True)
     dump(os.path.join("output", args.name, "evaluation.json"), meta)
     return meta

@@ -98,6 +98,8 @@ def load():
     ns.generate_patch_image = _pre.generate_patch_image
     ns.gen_trans_from_patch_cv = _pre.gen_trans_from_patch_cv
     ns.trans_point2d = _pre.trans_point2d
+    ns.augmentation = _pre.augmentation
+    ns.preprocessing = _pre          # module handle: tests pin get_aug_config to fixed draws
     from src.tools import dataset as _ds
     ns.CustomDataset = _ds.CustomDataset
     ns.generate_target = lambda joints: _ds.CustomDataset.generate_target(None, joints)

@@ -426,7 +426,7 @@ def gaussian_table(sigma):
     return np.exp(-((x - c) ** 2 + (y - c) ** 2) / (2 * sigma ** 2)).astype(np.float32)
 
 
-def generate_target(joints, num_joints=21, heatmap_hw=(64, 64), feat_stride=(4, 4), sigma=2):
+def generate_target(joints, num_joints=21, heatmap_hw=(64, 64), feat_stride=(4, 4), sigma=2, use_vis=False):
     """src/tools/dataset.py:165-212 (verbatim copies at src/utils/dataset_loader.py:236-286,
     :370-420, src/datasets/frei_dataloader.py:340-390), parametrised.  At the defaults it is
     the reference; other geometries follow upstream HRNet (tmp_size = 3 sigma) -- PARITY
@@ -434,10 +434,17 @@ def generate_target(joints, num_joints=21, heatmap_hw=(64, 64), feat_stride=(4, 
 
     Returns (target f32[J,H,W], target_weight f32[J,1]); the reference returns only the
     first (its target_weight is computed and dropped, dataset.py:171,185,212).
+
+    ``use_vis`` -- PARITY UNPINNED, not in the reference (which never looks at visibility): upstream HRNet's
+    JointsDataset.generate_target, the semantics BASELINE.json's north star names: ``target_weight[:, 0] =
+    joints_vis[:, 0]`` (third joint column), zeroed when the window leaves the map, and the Gaussian is pasted
+    only ``if target_weight > 0.5``.  With ``use_vis=False`` (or all-visible joints) it is the function above.
     """
     H, W = heatmap_hw
     joints = torch.as_tensor(joints, dtype=torch.float32)
     weight = np.ones((num_joints, 1), dtype=np.float32)
+    if use_vis:
+        weight[:, 0] = joints[:, 2].numpy()
     target = np.zeros((num_joints, H, W), dtype=np.float32)
     tmp = int(sigma * 3)
     for j in range(num_joints):
@@ -447,6 +454,8 @@ def generate_target(joints, num_joints=21, heatmap_hw=(64, 64), feat_stride=(4, 
         br = (mu_x + tmp + 1, mu_y + tmp + 1)
         if ul[0] >= W or ul[1] >= H or br[0] < 0 or br[1] < 0:
             weight[j] = 0
+            continue
+        if use_vis and not weight[j, 0] > 0.5:
             continue
         size = 2 * tmp + 1
         x = np.arange(0, size, 1, np.float32)
@@ -795,3 +804,28 @@ def pred_test_meta(meta, T_list, method):
     pck_t = np.array([(np.count_nonzero(nd < T) / total) * 100 for T in thr])
     auc = _trapz(pck_t, thr) / (norm_factor + sys.float_info.epsilon)
     return auc, diff.mean()
+
+
+# ----------------------------------------------------------------------------
+# a-1 (keypoint half)  augmentation()  src/utils/preprocessing.py:83-90
+# ----------------------------------------------------------------------------
+
+def augment_keypoints(joint_coord, joint_valid, trans, do_flip, orig_w, input_hw, right=None, left=None):
+    """The keypoint half of ``augmentation`` (src/utils/preprocessing.py:83-90), same statements in the same order:
+    mirror x about the original image width and swap the right / left joint blocks (coordinates and validity) when
+    flipped, ``trans_point2d`` every joint with the float32 crop matrix (float64 dot, stored into the float32 array),
+    then ``joint_valid *= (0 <= x < W_in) * (0 <= y < H_in)``.  ``right`` / ``left``: index arrays of the two hands
+    (``joint_type`` of the InterHand lineage); None for a single-hand skeleton (nothing to swap).
+    Returns (joint_coord f32[J,2+], joint_valid f32[J])."""
+    joint_coord = np.array(joint_coord, dtype=np.float32, copy=True)
+    joint_valid = np.array(joint_valid, dtype=np.float32, copy=True)
+    if do_flip:
+        joint_coord[:, 0] = orig_w - joint_coord[:, 0] - 1
+        if right is not None:
+            joint_coord[right], joint_coord[left] = joint_coord[left].copy(), joint_coord[right].copy()
+            joint_valid[right], joint_valid[left] = joint_valid[left].copy(), joint_valid[right].copy()
+    for i in range(len(joint_coord)):
+        joint_coord[i, :2] = trans_point2d(joint_coord[i, :2], trans)
+        joint_valid[i] = joint_valid[i] * (joint_coord[i, 0] >= 0) * (joint_coord[i, 0] < input_hw[1]) * \
+            (joint_coord[i, 1] >= 0) * (joint_coord[i, 1] < input_hw[0])
+    return joint_coord, joint_valid

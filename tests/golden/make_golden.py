@@ -274,6 +274,41 @@ def make_frei(ns):
          crops=np.stack(crops))
 
 
+def make_augment(ns):
+    """augmentation() (src/utils/preprocessing.py:65-92) with get_aug_config pinned to fixed draws: the transformed
+    key points and joint_valid for two-hand (42 joints, right / left swap) and single-hand (21 joints) skeletons."""
+    rng = np.random.default_rng(77)
+    pre = ns.preprocessing
+    keep = pre.get_aug_config
+    cases = []
+    try:
+        for n_j in (42, 21):
+            jt = {"right": np.arange(0, 21), "left": np.arange(21, 42)} if n_j == 42 else \
+                 {"right": np.arange(0, 0), "left": np.arange(0, 0)}
+            for _ in range(12):
+                img = rng.integers(0, 256, (240, 320, 3), dtype=np.uint8)
+                jc = rng.uniform(-20, 340, (n_j, 3)).astype(np.float32)
+                jv = (rng.uniform(size=n_j) < 0.8).astype(np.float32)
+                bbox = np.array([rng.uniform(0, 80), rng.uniform(0, 60), rng.uniform(120, 220), rng.uniform(120, 180)], np.float32)
+                cfgd = ([float(rng.uniform(-0.15, 0.15)), float(rng.uniform(-0.15, 0.15))], float(rng.uniform(0.75, 1.25)),
+                        float(rng.uniform(-90, 90)) if rng.uniform() < 0.6 else 0.0, bool(rng.uniform() < 0.5),
+                        rng.uniform(0.8, 1.2, 3))
+                pre.get_aug_config = lambda c=cfgd: c
+                _img, jc_o, jv_o, _ht, inv = pre.augmentation(img, bbox.copy(), jc, jv.copy(), np.array([1.0, 0.0], np.float32),
+                                                             "train", jt)
+                b2 = bbox.copy()
+                b2[0] += b2[2] * cfgd[0][0]; b2[1] += b2[3] * cfgd[0][1]
+                _p, trans, _inv = ns.generate_patch_image(img, b2, cfgd[3], cfgd[1], cfgd[2], (256, 256))
+                cases.append((n_j, jc, jv, trans, cfgd[3], jc_o, jv_o))
+    finally:
+        pre.get_aug_config = keep
+    for n_j in (42, 21):
+        sel = [c for c in cases if c[0] == n_j]
+        save(f"augment{n_j}.npz", joints=np.stack([c[1] for c in sel]), valid=np.stack([c[2] for c in sel]),
+             trans=np.stack([c[3] for c in sel]), flip=np.array([c[4] for c in sel]), orig_w=np.int64(320),
+             joints_out=np.stack([c[5] for c in sel]), valid_out=np.stack([c[6] for c in sel]))
+
+
 def main():
     if not rb.available():
         raise SystemExit("reference tree not mounted; fixtures can only be generated in the build container")
@@ -286,6 +321,7 @@ def main():
     make_warp(ns)
     make_resize()
     make_frei(ns)
+    make_augment(ns)
     import cv2
     import torchvision
     with open(os.path.join(HERE, "VERSIONS.json"), "w") as f:

@@ -35,7 +35,7 @@ def test_version_and_error_text():
 def test_argument_validation_needs_no_device():
     """Argument errors are reported before any CUDA call (negative codes)."""
     lib = _lib.load()
-    assert lib.lh_gen_targets(None, 2, 1, 21, 64, 64, 4.0, 4.0, 0, None, 13, None, None, None) == -2
+    assert lib.lh_gen_targets(None, 2, 1, 21, 64, 64, 4.0, 4.0, 0, 0, None, 13, None, None, None) == -2
     assert lib.lh_decode(None, 1, 21, 64, 64, 4.0, 0, None, None, None, None, None) == -2
     assert lib.lh_jmse_loss(None, None, None, 1, 21, 64, 64, None, None, None, None, None) == -2
     assert lib.lh_pck_epe_batch(None, None, 2, 1, 21, 0.2, 0, 0, None, None, None) == -2
@@ -44,7 +44,7 @@ def test_argument_validation_needs_no_device():
 
 def test_struct_layout_matches_header():
     # offsets the C side relies on: pointers first, then N (int64), then int32s / floats
-    assert ctypes.sizeof(_lib.HeatmapArgs) == 17 * 8 + 8 + 8 * 4 + 4 * 4 + 4 + 4   # 17 pointers, N, 8 int32, 4 float, int32, pad
+    assert ctypes.sizeof(_lib.HeatmapArgs) == 17 * 8 + 8 + 8 * 4 + 4 * 4 + 4 + 4   # 17 pointers, N, 8 int32, 4 float, 2 int32
     assert _lib.HeatmapArgs.N.offset == 136
     assert ctypes.sizeof(_lib.PipelineCfg) == 14 * 4 + 2 * 4 + 6 * 4
     assert ctypes.sizeof(_lib.PipelineIO) == 10 * 8

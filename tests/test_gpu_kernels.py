@@ -292,3 +292,59 @@ def test_pck_curve_bbox_computed_on_device_and_large_random(ops):
             assert np.array_equal(np.asarray(got[k][2]), np.asarray(want[k][2]))
             assert got[k][0] == pytest.approx(want[k][0], rel=1e-12)
             assert got[k][1] == pytest.approx(want[k][1], rel=1e-9)
+
+
+def test_transform_joints_golden_bitexact(ops):
+    """lh_transform_joints against fixtures produced by the reference's augmentation() (flip mirror, right / left swap,
+    trans_point2d, joint_valid in-image test; src/utils/preprocessing.py:83-90)."""
+    for n_j in (42, 21):
+        g = golden(f"augment{n_j}.npz")
+        swap = None
+        if n_j == 42:
+            swap = cu(np.concatenate([np.arange(21, 42), np.arange(0, 21)]).astype(np.int32))
+        out, valid = ops.transform_joints(cu(g["joints"]), cu(g["trans"].astype(np.float64)), (256, 256),
+                                          flip=cu(g["flip"].astype(np.uint8)), orig_w=int(g["orig_w"]), swap=swap,
+                                          valid=cu(g["valid"]))
+        assert np.array_equal(out[..., :2].cpu().numpy(), g["joints_out"][..., :2])
+        assert np.array_equal(valid.cpu().numpy(), g["valid_out"]) and np.array_equal(out[..., 2].cpu().numpy(), g["valid_out"])
+
+
+def test_targets_and_fused_pass_with_visibility_vs_oracle(ops):
+    """north_star item (2): target_weight = visibility * in-bounds (upstream HRNet; parity unpinned), masking the loss."""
+    rng = np.random.default_rng(31)
+    for (S, H, sigma, n) in ((256, 64, 2, 6), (224, 56, 2, 3)):
+        stride = S / H
+        j = edge_like(rng, n, S)
+        vis = (rng.uniform(size=(n, 21, 1)) < 0.7).astype(np.float32)
+        j3 = np.concatenate([j, vis], -1).astype(np.float32)
+        want = [R.generate_target(j3[i], 21, (H, H), (stride, stride), sigma, use_vis=True) for i in range(n)]
+        wt, ww = np.stack([w[0] for w in want]), np.stack([w[1] for w in want])
+        tgt, wgt = ops.gen_targets(cu(j3), (H, H), (stride, stride), sigma, use_vis=True)
+        assert np.array_equal(tgt.cpu().numpy(), wt) and np.array_equal(wgt.cpu().numpy(), ww)
+        assert (ww == 0).any() and (ww == 1).any()
+        # off: the reference's behaviour (visibility ignored)
+        t0, w0 = ops.gen_targets(cu(j3), (H, H), (stride, stride), sigma)
+        assert np.array_equal(t0.cpu().numpy(), np.stack([R.generate_target(j[i], 21, (H, H), (stride, stride), sigma)[0] for i in range(n)]))
+        # fused pass: targets from the joints, loss masked by the same weights
+        pred = (wt + 0.1 * rng.standard_normal(wt.shape)).astype(np.float32)
+        loss, grad = R.joints_mse_loss_and_grad(pred, wt, ww, use_target_weight=True)
+        out = ops.heatmap_fused(cu(pred), cu(j3), sigma=sigma, feat_stride=(stride, stride), want_target=True,
+                                use_target_weight=True, use_vis=True, out_scale=stride)
+        assert np.array_equal(out["target"].cpu().numpy(), wt) and np.array_equal(out["weight"].cpu().numpy(), ww)
+        assert out["loss"].item() == pytest.approx(loss, rel=1e-5)
+        np.testing.assert_allclose(out["grad"].cpu().numpy(), grad, rtol=1e-5, atol=1e-12)
+
+
+def edge_like(rng, n, S):
+    j = rng.uniform(0, S, (n, 21, 2)).astype(np.float32)
+    off = rng.uniform(size=(n, 21)) < 0.15
+    j[off] = rng.uniform(-S / 4, 5 * S / 4, (int(off.sum()), 2)).astype(np.float32)
+    return j
+
+
+def test_bbox_diag_vs_oracle(ops):
+    rng = np.random.default_rng(8)
+    gt = rng.uniform(0, 256, (37, 21, 3)).astype(np.float32)
+    gt[3, :, :2] = 5.0                                       # zero diagonal
+    got = ops.bbox_diag(cu(gt)).cpu().numpy()
+    assert got.tolist() == R.bbox_diag_store(torch.from_numpy(gt))

@@ -144,3 +144,35 @@ def test_pred_store_wire_format_and_eval_sweep(tmp_path, monkeypatch):
     first = lines[0].split(";")
     k0 = next(iter(out))
     assert first[0] == k0 and first[1] == "tiny/run" and first[2] == "{:.2f}".format(out[k0][0]) and len(first) == 4 + 100 + 1
+
+
+def test_gpu_collate_eval_phase_feeds_pred_store(tmp_path, monkeypatch):
+    """eval_set.__getitem__ (phase "eval", src/tools/dataset.py:257-300) as a device collate: item shape, key-point
+    scaling, and the batch goes straight into pred_store (src/utils/argparser.py:246-281)."""
+    from torchvision import transforms
+    from lighthand_b200.tools.dataset import GpuCollate
+    from lighthand_b200.utils import argparser as A
+    monkeypatch.chdir(tmp_path)
+    rng = np.random.default_rng(12)
+    names = list(A.POSE_CATEGORIES)
+    samples = []
+    for i in range(6):
+        img = rng.integers(0, 256, (224, 224, 3), dtype=np.uint8)
+        joint = rng.uniform(0.05, 0.95, (21, 3)).astype(np.float32)
+        vis = (rng.uniform(size=21) < 0.8).astype(np.float32)
+        samples.append((img, joint, vis, names[i % 4], i))
+    coll = GpuCollate(image_size=64, phase="eval")
+    images, joint_2d_v, (pose, idx) = coll(samples)
+    trans = transforms.Compose([transforms.ToTensor(), transforms.Resize((64, 64), antialias=False),
+                                transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    want_img = torch.stack([trans(s[0]) for s in samples])
+    assert torch.allclose(images.cpu(), want_img, rtol=1e-5, atol=1e-5)
+    want_j = torch.stack([torch.cat([torch.tensor(s[1])[:, :2] * 64, torch.tensor(s[2])[:, None]], 1) for s in samples])
+    assert torch.equal(joint_2d_v.cpu(), want_j) and pose == [s[3] for s in samples] and idx == list(range(6))
+    torch.manual_seed(1)
+    model = TinyNet().cuda().eval()
+    bar = types.SimpleNamespace(update=lambda k: None)
+    meta = A.pred_store(types.SimpleNamespace(name="tiny/eval"), [(images, joint_2d_v, (pose, idx))], model, bar)
+    assert sum(len(v["bb"]) for v in meta.values()) == 6
+    for k, name in enumerate(pose):
+        assert meta[name]["gt"][k // 4] == want_j[k].tolist()

@@ -197,3 +197,28 @@ def test_cv2_models_of_the_frei_stages():
         assert np.array_equal(R.warp_affine_model(img.astype(np.float32), M, sh, sw).astype(np.float64), a)
         np.testing.assert_allclose(R.cv2_resize_linear_model(img, 56, 56),
                                    cv2.resize(img, (56, 56), interpolation=cv2.INTER_LINEAR), rtol=0, atol=1e-9)
+
+
+def test_augment_keypoints_matches_reference_bitexact():
+    """Keypoint half of augmentation() (src/utils/preprocessing.py:83-90): fixtures made by running the reference with
+    get_aug_config pinned (tests/golden/make_golden.py: make_augment)."""
+    for n_j in (42, 21):
+        g = golden(f"augment{n_j}.npz")
+        right, left = (np.arange(0, 21), np.arange(21, 42)) if n_j == 42 else (None, None)
+        assert g["flip"].any() and not g["flip"].all()
+        for i in range(len(g["joints"])):
+            jc, jv = R.augment_keypoints(g["joints"][i], g["valid"][i], g["trans"][i], bool(g["flip"][i]), int(g["orig_w"]),
+                                         (256, 256), right, left)
+            assert np.array_equal(jc, g["joints_out"][i]) and np.array_equal(jv, g["valid_out"][i])
+
+
+def test_generate_target_use_vis_reduces_to_reference_when_all_visible():
+    g = golden("targets.npz")
+    j3 = np.concatenate([g["joints"], np.ones((*g["joints"].shape[:2], 1), np.float32)], -1)
+    for i in range(4):
+        t0, w0 = R.generate_target(g["joints"][i])
+        t1, w1 = R.generate_target(j3[i], use_vis=True)
+        assert np.array_equal(t0, t1) and np.array_equal(w0, w1)
+    j3[0, 3, 2] = 0.0
+    t, w = R.generate_target(j3[0], use_vis=True)
+    assert not t[3].any() and w[3, 0] == 0.0 and np.array_equal(t[4], R.generate_target(g["joints"][0])[0][4])
