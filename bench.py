@@ -274,6 +274,52 @@ def h2d_ceiling(nbytes, dev, world, dist, reps=12):
     return nbytes * reps / dt / 1e9
 
 
+def jpeg_leg(hp, host_sets, B, S, Ke, args):
+    import cv2
+    import torch
+    rng = np.random.default_rng(4242)
+
+    def smooth(h, w):
+        base = rng.uniform(0, 255, (6, 6, 3)).astype(np.float32)
+        img = cv2.resize(base, (w, h), interpolation=cv2.INTER_CUBIC)
+        for _ in range(4):
+            x0, y0 = int(rng.integers(0, w - 16)), int(rng.integers(0, h - 16))
+            img[y0:y0 + int(rng.integers(8, h // 2)), x0:x0 + int(rng.integers(8, w // 2))] += rng.uniform(-60, 60, 3)
+        img += rng.normal(0, 3, img.shape)
+        return np.clip(img, 0, 255).astype(np.uint8)
+
+    pool = [cv2.imencode(".jpg", smooth(S, S), [cv2.IMWRITE_JPEG_QUALITY, 90])[1].tobytes() for _ in range(64)]
+    sets = [[pool[(i * 7 + k) % len(pool)] for i in range(B)] for k in range(2)]
+    nbytes = float(np.mean([sum(len(b) for b in s_) for s_ in sets]))
+    outs = [hp.new_outputs(), hp.new_outputs()]
+    res = {"h2d_bytes_per_step": nbytes + B * 48 + B + B * 21 * 8, "jpeg_quality": 90, "image_bytes_mean": nbytes / B,
+           "raw_bytes_per_image": S * S * 3, "data": "synthetic natural-like images (smooth colour field + edges + noise), 4:2:0"}
+    for backend in ("hardware", "gpu_hybrid", "hybrid"):
+        try:
+            def run(n_steps):
+                pend = None
+                for i in range(n_steps):
+                    _imgs, M, joints, fl = host_sets[i % 2]
+                    cur = hp.submit_jpeg(sets[i % 2], M, joints, flip=fl, out=outs[i % 2], backend=backend)
+                    if pend is not None:
+                        hp.wait(pend[0])
+                    pend = cur
+                hp.wait(pend[0])
+            run(3)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n_steps = max(4, min(Ke, 30))
+            run(n_steps)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            res.update({"value": B * n_steps / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / n_steps, "steps": n_steps,
+                        "backend": backend})
+            break
+        except Exception as ex:          # backend not available on this part: try the next one
+            res.setdefault("backends_unavailable", []).append(f"{backend}: {type(ex).__name__}")
+    return res
+
+
 def run_ours(args):
     wl = WORKLOADS[args.workload]
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -462,6 +508,11 @@ def run_ours(args):
                "note": "lh_pipeline_submit/wait (C ABI) from pinned host buffers, double-buffered, H2D + K1 of step i+1 overlap the "
                        "loss stage of step i; pred stays device-resident (it is the backbone's output); ceiling = plain pinned "
                        "cudaMemcpyAsync of the same bytes on all ranks at once"}
+        # ---- e2e with COMPRESSED input (f-4): the same step fed with JPEG bit-streams, decoded on the device by nvJPEG
+        # into K1's source buffer.  Natural-like synthetic images (uniform noise does not compress); reported BESIDE the
+        # raw-uint8 number, not instead of it: at 256x256 the decoder, not PCIe, is the limit.
+        if args.jpeg and world == 1:
+            e2e["jpeg"] = jpeg_leg(hp, host_sets, B, S, Ke, args)
         hp.close()
 
     if rank != 0:
@@ -671,6 +722,7 @@ def main():
     ap.add_argument("--repeats", type=int, default=0, help="repetitions of the K-step timed region (0: enough for ~250 ms)")
     ap.add_argument("--total", type=int, default=0, help="C4: evaluate this many samples instead of 99,792")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-jpeg", dest="jpeg", action="store_false", help="skip the compressed-input e2e leg (f-4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=70)
     ap.add_argument("--e2e-steps", type=int, default=200)

@@ -36,6 +36,7 @@ extern "C" {
 #define LH_ENOMEM       (-5)  /* workspace too small / allocation failed (pipeline ctx) */
 #define LH_ENODEVICE    (-6)  /* no sm_100 device */
 #define LH_ENCCL        (-7)  /* NCCL missing (libnccl.so.2 could not be loaded) or an NCCL call failed */
+#define LH_EJPEG        (-8)  /* nvJPEG missing (libnvjpeg.so.12), backend unavailable, or a bit-stream it cannot decode */
 
 typedef void* lh_stream_t; /* cudaStream_t */
 
@@ -304,6 +305,27 @@ int lh_color_jitter_normalize(const float* src, const lh_jitter_params* params, 
                               const float* mean_std, float* dst, double* ws, lh_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * f-4  JPEG decode on the device: N baseline JPEG bit-streams (host memory) -> dst dev
+ * [N, h, w, 3] RGB uint8 (HWC: what lh_warp_normalize / lh_frei_rgb_processing read), asynchronous on `stream`.
+ * Replaces img_from_base64 (src/utils/tsv_file_ops.py:21-28: cv2.imdecode) + the BGR2RGB of get_image
+ * (src/datasets/frei_dataloader.py:195-204); the base64 / TSV side is lighthand_b200/utils/tsv_file.py.
+ * Decoder = nvJPEG, bound at run time; not bit-identical to libjpeg-turbo (IDCT / chroma upsampling accuracy is not
+ * part of the JPEG standard): the tolerance is stated in DESIGN.md and tested in tests/test_gpu_jpeg.py.
+ * backend: nvJPEG's (DEFAULT, HYBRID = Huffman on the CPU, GPU_HYBRID = Huffman on the GPU, HARDWARE = the NVJPG engine).
+ * Every bit-stream of a batch must have the size w x h (else LH_EINVAL).  The data / sizes arrays and the bit-streams
+ * must stay valid until the stream has passed the call.
+ * ------------------------------------------------------------------------------------------ */
+#define LH_JPEG_BACKEND_DEFAULT    0
+#define LH_JPEG_BACKEND_HYBRID     1
+#define LH_JPEG_BACKEND_GPU_HYBRID 2
+#define LH_JPEG_BACKEND_HARDWARE   3
+typedef struct lh_jpeg lh_jpeg;
+int lh_jpeg_create(int device, int backend, int cpu_threads, lh_jpeg** out);
+void lh_jpeg_destroy(lh_jpeg* j);
+int lh_jpeg_decode_batch(lh_jpeg* j, const uint8_t* const* data, const size_t* sizes, int n, int w, int h,
+                         uint8_t* dst, int64_t dst_img_stride, int dst_pitch, lh_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Host-buffer pipeline context (what a non-torch host binds; also the e2e benchmark path).
  * Owns device buffers, pinned staging and three streams; one step is
  *   data stage   H2D -> K1 -> input[slot]                       (copy + data streams)
@@ -366,6 +388,11 @@ int lh_pipeline_wait(lh_pipeline* p, int slot);
  *   lh_pipeline_wait(p, slot); */
 int lh_pipeline_submit_inputs(lh_pipeline* p, const lh_pipeline_io* io, int* slot_out);
 int lh_pipeline_submit_loss(lh_pipeline* p, int slot);
+/* data stage from COMPRESSED input (f-4): `data` / `sizes` = batch JPEG bit-streams of src_w x src_h (host memory; must
+ * stay valid until the slot is waited for); io->images is ignored; the context creates its lh_jpeg with `jpeg_backend`
+ * on first use.  PCIe then carries the compressed bytes. */
+int lh_pipeline_submit_inputs_jpeg(lh_pipeline* p, const uint8_t* const* data, const size_t* sizes, int jpeg_backend,
+                                   const lh_pipeline_io* io, int* slot_out);
 void* lh_pipeline_loss_stream(lh_pipeline* p);   /* cudaStream_t */
 /* multi-GPU: SUM the running accumulators over `comm` (lh_comm_init), ordered after the last submitted loss stage;
  * lh_pipeline_read_metrics = synchronous read of counts u64[4] / sums f64[4] (see lh_pipeline_io) */

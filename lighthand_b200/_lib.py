@@ -105,6 +105,7 @@ PROTOTYPES = {
     "lh_pipeline_wait": (c_i, [c_p, c_i]),
     "lh_pipeline_submit_inputs": (c_i, [c_p, C.POINTER(PipelineIO), C.POINTER(c_i)]),
     "lh_pipeline_submit_loss": (c_i, [c_p, c_i]),
+    "lh_pipeline_submit_inputs_jpeg": (c_i, [c_p, c_p, c_p, c_i, C.POINTER(PipelineIO), C.POINTER(c_i)]),
     "lh_pipeline_loss_stream": (c_p, [c_p]),
     "lh_pipeline_input_dev_slot": (c_p, [c_p, c_i]),
     "lh_pipeline_allreduce_metrics": (c_i, [c_p, c_p]),
@@ -113,6 +114,9 @@ PROTOTYPES = {
     "lh_pipeline_launches_per_step": (c_i, [c_p]),
     "lh_host_alloc": (c_p, [C.c_size_t]),
     "lh_host_free": (None, [c_p]),
+    "lh_jpeg_create": (c_i, [c_i, c_i, c_i, C.POINTER(c_p)]),
+    "lh_jpeg_destroy": (None, [c_p]),
+    "lh_jpeg_decode_batch": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_i64, c_i, c_p]),
     "lh_comm_unique_id": (c_i, [c_p]),
     "lh_comm_init": (c_i, [c_p, c_i, c_i, c_i, C.POINTER(c_p)]),
     "lh_comm_destroy": (c_i, [c_p]),

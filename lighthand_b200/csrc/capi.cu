@@ -12,6 +12,7 @@ extern "C" const char* lh_strerror(int code) {
         case LH_EUNSUPPORTED: return "lighthand_b200: geometry not supported by the sm_100a kernels";
         case LH_ENOMEM: return "lighthand_b200: out of memory / workspace too small";
         case LH_ENODEVICE: return "lighthand_b200: no CUDA device of compute capability 10.x";
+        case LH_EJPEG: return "lighthand_b200: nvJPEG unavailable (libnvjpeg.so.12 / backend) or an undecodable bit-stream";
         case LH_ENCCL: return "lighthand_b200: NCCL unavailable (libnccl.so.2) or an NCCL call failed";
         default: break;
     }

@@ -55,6 +55,8 @@ struct lh_pipeline {
     double* d_sums = nullptr;
     size_t out_bytes = 0, off_coords = 0, off_maxvals = 0, off_counts = 0, off_sums = 0;
     unsigned long long step = 0;
+    lh_jpeg* jpeg = nullptr;    // created by the first lh_pipeline_submit_inputs_jpeg
+    int jpeg_backend = -1;
 };
 
 #define PCHK(x)                                      \
@@ -79,6 +81,7 @@ extern "C" void lh_pipeline_destroy(lh_pipeline* p) {
     }
     cudaFree(p->d_pred); cudaFree(p->d_target); cudaFree(p->d_grad);
     cudaFree(p->d_table); cudaFree(p->d_lut); cudaFree(p->d_ws); cudaFree(p->d_counts); cudaFree(p->d_sums);
+    if (p->jpeg) lh_jpeg_destroy(p->jpeg);
     if (p->s_copy) cudaStreamDestroy(p->s_copy);
     if (p->s_data) cudaStreamDestroy(p->s_data);
     if (p->s_comp) cudaStreamDestroy(p->s_comp);
@@ -170,8 +173,9 @@ extern "C" int lh_pipeline_reset_metrics(lh_pipeline* p) {
 
 // data stage of one step into slot (step % 2): H2D on the copy stream, K1 on the data stream; the loss stream is
 // made to wait for K1, so whatever the caller enqueues on lh_pipeline_loss_stream() next (the backbone) sees the input
-extern "C" int lh_pipeline_submit_inputs(lh_pipeline* p, const lh_pipeline_io* io, int* slot_out) {
-    if (!p || !io || !io->images || !io->joints || !slot_out) return LH_ENULL;
+static int submit_inputs_impl(lh_pipeline* p, const lh_pipeline_io* io, const uint8_t* const* jpeg_data,
+                              const size_t* jpeg_sizes, int* slot_out) {
+    if (!p || !io || !(io->images || jpeg_data) || !io->joints || !slot_out) return LH_ENULL;
     const lh_pipeline_cfg& c = p->cfg;
     if (c.interp != LH_INTERP_TORCH && !io->fwd_affine) return LH_ENULL;
     const int si = (int)(p->step % kSlots);
@@ -182,7 +186,14 @@ extern "C" int lh_pipeline_submit_inputs(lh_pipeline* p, const lh_pipeline_io* i
     int rc = LH_OK;
     PCHK(cudaSetDevice(c.device));
     // H2D on the copy stream (the slot's previous consumer finished: its ev_done was waited by the host)
-    PCHK(cudaMemcpyAsync(s.d_images, io->images, N * img_bytes, cudaMemcpyHostToDevice, p->s_copy));
+    if (jpeg_data) {
+        // compressed input: PCIe carries the JPEG bytes, nvJPEG decodes straight into the slot's uint8 HWC source buffer
+        rc = lh_jpeg_decode_batch(p->jpeg, jpeg_data, jpeg_sizes, (int)N, c.src_w, c.src_h, s.d_images, (int64_t)img_bytes,
+                                  c.src_w * 3, p->s_copy);
+        if (rc) goto fail;
+    } else {
+        PCHK(cudaMemcpyAsync(s.d_images, io->images, N * img_bytes, cudaMemcpyHostToDevice, p->s_copy));
+    }
     if (io->fwd_affine) PCHK(cudaMemcpyAsync(s.d_affine, io->fwd_affine, N * 6 * sizeof(double), cudaMemcpyHostToDevice, p->s_copy));
     if (io->flip) PCHK(cudaMemcpyAsync(s.d_flip, io->flip, N, cudaMemcpyHostToDevice, p->s_copy));
     PCHK(cudaMemcpyAsync(s.d_joints, io->joints, N * J * 2 * sizeof(float), cudaMemcpyHostToDevice, p->s_copy));
@@ -204,6 +215,29 @@ extern "C" int lh_pipeline_submit_inputs(lh_pipeline* p, const lh_pipeline_io* i
     return LH_OK;
 fail:
     return rc;
+}
+
+extern "C" int lh_pipeline_submit_inputs(lh_pipeline* p, const lh_pipeline_io* io, int* slot_out) {
+    if (!io || !io->images) return LH_ENULL;
+    return submit_inputs_impl(p, io, nullptr, nullptr, slot_out);
+}
+
+// the same data stage fed with N JPEG bit-streams (io->images is ignored): decode on the device, then K1
+extern "C" int lh_pipeline_submit_inputs_jpeg(lh_pipeline* p, const uint8_t* const* data, const size_t* sizes,
+                                              int jpeg_backend, const lh_pipeline_io* io, int* slot_out) {
+    if (!p || !data || !sizes) return LH_ENULL;
+    if (p->jpeg && p->jpeg_backend != jpeg_backend) {       // another backend asked for: start over
+        cudaSetDevice(p->cfg.device);
+        cudaStreamSynchronize(p->s_copy);
+        lh_jpeg_destroy(p->jpeg);
+        p->jpeg = nullptr;
+    }
+    if (!p->jpeg) {
+        const int rc = lh_jpeg_create(p->cfg.device, jpeg_backend, 1, &p->jpeg);
+        if (rc) return rc;
+        p->jpeg_backend = jpeg_backend;
+    }
+    return submit_inputs_impl(p, io, data, sizes, slot_out);
 }
 
 // loss stage of the step in `si` on the loss stream: [pred H2D] -> fused K2+K3+K4+K5 -> D2H of the results

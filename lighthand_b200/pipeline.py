@@ -437,6 +437,21 @@ class HostPipeline:
         check(self.lib.lh_pipeline_submit_inputs(self._h, C.byref(io), C.byref(slot)), "lh_pipeline_submit_inputs")
         return slot.value, out, (io, images, fwd_affine, joints, flip, pred)
 
+    def submit_jpeg(self, streams, fwd_affine, joints, flip=None, pred=None, out=None, backend: str = "gpu_hybrid"):
+        """One whole step from COMPRESSED input: ``streams`` = batch JPEG bit-streams (bytes) of src_hw; nvJPEG decodes
+        them on the device into the slot's source buffer, then K1 and the loss stage as in ``submit``."""
+        from .utils.tsv_file import JpegDecoder
+        out = out if out is not None else self.new_outputs()
+        io = self._io(None, fwd_affine, joints, flip, pred, out)
+        n = len(streams)
+        ptrs = (C.c_char_p * n)(*streams)
+        sizes = (C.c_size_t * n)(*[len(b) for b in streams])
+        slot = C.c_int(-1)
+        check(self.lib.lh_pipeline_submit_inputs_jpeg(self._h, ptrs, sizes, JpegDecoder.BACKENDS[backend], C.byref(io),
+                                                      C.byref(slot)), "lh_pipeline_submit_inputs_jpeg")
+        check(self.lib.lh_pipeline_submit_loss(self._h, slot.value), "lh_pipeline_submit_loss")
+        return slot.value, out, (io, streams, ptrs, sizes, fwd_affine, joints, flip, pred)
+
     def submit_loss(self, slot: int):
         check(self.lib.lh_pipeline_submit_loss(self._h, int(slot)), "lh_pipeline_submit_loss")
 

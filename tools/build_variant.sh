@@ -6,7 +6,7 @@ set -e
 tag=$1; shift
 cd "$(dirname "$0")/../lighthand_b200/csrc"
 mkdir -p build/var_$tag
-for f in capi heatmap metrics warp_normalize warp_tma frei_crop color_jitter pipeline comm; do
+for f in capi heatmap metrics warp_normalize warp_tma frei_crop color_jitter pipeline comm jpeg_decode; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC $@ -c $f.cu -o build/var_$tag/$f.o &
 done
 wait
