@@ -199,7 +199,7 @@ def load_peaks():
 def load_traffic(kernel_key):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (C2 only)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_final_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             t = json.load(f)["kernels"]
         for name, v in t.items():
             if kernel_key in name:
@@ -548,7 +548,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
                      "frac_of_nominal_8000GBps": achieved / 8000.0,      # north_star quotes the nominal HBM3e figure too
-                     "traffic": load_traffic("warp_tma" if dom[0] == "warp_normalize" else "heatmap_vec") if args.workload == "C2" and not args.batch else None,
+                     "traffic": load_traffic("warp_tma" if dom[0] == "warp_normalize" else "heatmap_warp") if args.workload == "C2" and not args.batch else None,
                      "traffic_note": "dram__bytes_read+write per launch, ncu --set full (profiles/r02_traffic.json); below the algorithmic bytes because part of the output is still dirty in the 126 MB L2 when the kernel ends",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dom[1], "avg_launch_ms": dom[2],
