@@ -14,8 +14,8 @@
 //     into a kStages-deep ring of shared-memory stages; full/empty mbarriers hand the stages over;
 //   * four CONSUMER warps render (lane = output column, a warp takes 8 tile rows) straight from the RAW bytes:
 //     three aligned LDS.32 per tap row, two funnel shifts + two PRMT give {R0 R1 G0 G1} / {B0 B1 - -}, and each
-//     channel's whole 2-D blend is two IDP.2A against the 16-bit weight pairs {wx0*wy, wx1*wy} (sum + 512 < 2^18);
-//     the >>10 and the int->float conversion are one funnel shift under the exponent of 2^23 and one FADD.
+//     channel's whole 2-D blend is two IDP.2A against the 16-bit weight pairs {32 wx0 wy, 32 wx1 wy} (cv2's own weights);
+//     the >>15 and the int->float conversion are one funnel shift under the exponent of 2^23 and one FADD.
 //
 // No staging instructions, no per-tile barrier, no global-load latency on the rendering warps.
 #include <cuda.h>   // CUtensorMap + enums (types only: the encoder is resolved through cudaGetDriverEntryPoint)
@@ -113,7 +113,9 @@ __device__ __forceinline__ void render_rows(const WarpParams& p, const StageInfo
         if (!GEO && j >= rows) break;
         const int X = x0v[j] + ad, Y = y0v[j] + bd;
         const int ix = X >> 10, iy = Y >> 10;
-        const uint32_t ax = (uint32_t)(X >> 5) & 31u, ay = (uint32_t)(Y >> 5) & 31u;
+        // horizontal weights stay scaled by 32 (ax32 = 32 * ax is a plain mask of X: one instruction less than shift + mask);
+        // the sum then carries cv2's own scale: (sum p * 32 wx wy + 2^14) >> 15, products still fit 16 bits (<= 32768)
+        const uint32_t ax32 = (uint32_t)X & 0x3e0u, ay = (uint32_t)(Y >> 5) & 31u;
         uint32_t t0x, t0y, t1x, t1y;     // {R0 R1 G0 G1}, {B0 B1 - -} of the upper / lower tap row
         if (STAGED) {
             const uint32_t o = (uint32_t)(iy * kBoxW) + ((uint32_t)(ix * 3) + org);   // byte address of the tap origin
@@ -129,19 +131,19 @@ __device__ __forceinline__ void render_rows(const WarpParams& p, const StageInfo
             const uint4 t = tma_taps_from_global(img, p.pitch, p.sw, p.sh, ix, iy);
             t0x = t.x; t0y = t.y; t1x = t.z; t1y = t.w;
         }
-        const uint32_t wxp = ax * 65535u + 32u;                  // 16-bit pair {32 - ax, ax}
-        const uint32_t w0 = wxp * (32u - ay), w1 = wxp * ay;     // {wx0*wy0, wx1*wy0}, {wx0*wy1, wx1*wy1}: each <= 1024
-        const uint32_t sr = __dp2a_lo(w1, t1x, __dp2a_lo(w0, t0x, 512u));
-        const uint32_t sg = __dp2a_hi(w1, t1x, __dp2a_hi(w0, t0x, 512u));
-        const uint32_t sb = __dp2a_lo(w1, t1y, __dp2a_lo(w0, t0y, 512u));
+        const uint32_t wxp = ax32 * 65535u + 1024u;              // 16-bit pair {32 (32 - ax), 32 ax}
+        const uint32_t w0 = wxp * (32u - ay), w1 = wxp * ay;     // cv2's weights 32 wx wy: {w00, w01}, {w10, w11}, each <= 32768
+        const uint32_t sr = __dp2a_lo(w1, t1x, __dp2a_lo(w0, t0x, 16384u));
+        const uint32_t sg = __dp2a_hi(w1, t1x, __dp2a_hi(w0, t0x, 16384u));
+        const uint32_t sb = __dp2a_lo(w1, t1y, __dp2a_lo(w0, t0y, 16384u));
         float o0, o1, o2;
         if (NORM == 2) {
-            o0 = s_lut[sr >> 10]; o1 = s_lut[256 + (sg >> 10)]; o2 = s_lut[512 + (sb >> 10)];
+            o0 = s_lut[sr >> 15]; o1 = s_lut[256 + (sg >> 15)]; o2 = s_lut[512 + (sb >> 15)];
         } else {
-            // (s >> 10) under the exponent of 2^23 in one funnel shift, minus 2^23: the exact float of the uint8 result
-            const float vr = __uint_as_float(__funnelshift_r(sr, 0x12Cu, 10)) - 8388608.0f;
-            const float vg = __uint_as_float(__funnelshift_r(sg, 0x12Cu, 10)) - 8388608.0f;
-            const float vb = __uint_as_float(__funnelshift_r(sb, 0x12Cu, 10)) - 8388608.0f;
+            // (s >> 15) under the exponent of 2^23 in one funnel shift, minus 2^23: the exact float of the uint8 result
+            const float vr = __uint_as_float(__funnelshift_r(sr, 0x2580u, 15)) - 8388608.0f;
+            const float vg = __uint_as_float(__funnelshift_r(sg, 0x2580u, 15)) - 8388608.0f;
+            const float vb = __uint_as_float(__funnelshift_r(sb, 0x2580u, 15)) - 8388608.0f;
             if (NORM == 1) { o0 = fmaf(vr, na0, nb0); o1 = fmaf(vg, na1, nb1); o2 = fmaf(vb, na2, nb2); }
             else { o0 = vr; o1 = vg; o2 = vb; }
         }
