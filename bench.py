@@ -262,16 +262,19 @@ def h2d_ceiling(nbytes, dev, world, dist, reps=12):
         for i in range(2):
             dst[i].copy_(src[i], non_blocking=True)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    with torch.cuda.stream(st):
-        for i in range(reps):
-            dst[i % 2].copy_(src[i % 2], non_blocking=True)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    return nbytes * reps / dt / 1e9
+    best = 0.0
+    for _ in range(3):                  # best of three passes: a ceiling, not an average
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(st):
+            for i in range(reps):
+                dst[i % 2].copy_(src[i % 2], non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        best = max(best, nbytes * reps / dt / 1e9)
+    return best
 
 
 def jpeg_leg(hp, host_sets, B, S, Ke, args):

@@ -7,26 +7,30 @@
 // Same arithmetic as warp_pairs_kernel (warp_normalize.cu; SURVEY.md Appendix A: OpenCV's double-precision matrix
 // inversion, 1/32-px fixed-point grid, (sum p*w + 2^14) >> 15), different machine mapping:
 //
-//   * persistent CTAs (SMs x resident CTAs), static round-robin over the 32x32 output tiles;
+//   * persistent CTAs (4 per SM), static round-robin over the 32x32 output tiles;
 //   * one PRODUCER warp per CTA computes a tile's coordinate tables and source footprint (FP64, off the critical
 //     path) and fetches the footprint with ONE 3-D TMA load (cp.async.bulk.tensor over a u8 tensor map
 //     [N][src_h][3*src_w]; out-of-image bytes arrive as zeros = cv2's constant border, no predicates anywhere)
-//     into a kStages-deep ring of shared-memory stages; full/empty mbarriers hand the stages over;
+//     into a kStages-deep (3) ring of shared-memory stages; full/empty mbarriers hand the stages over;
 //   * four CONSUMER warps render (lane = output column, a warp takes 8 tile rows) straight from the RAW bytes:
 //     three aligned LDS.32 per tap row, two funnel shifts + two PRMT give {R0 R1 G0 G1} / {B0 B1 - -}, and each
 //     channel's whole 2-D blend is two IDP.2A against the 16-bit weight pairs {32 wx0 wy, 32 wx1 wy} (cv2's own weights);
 //     the >>15 and the int->float conversion are one funnel shift under the exponent of 2^23 and one FADD.
 //
 // No staging instructions, no per-tile barrier, no global-load latency on the rendering warps.
+#include <cstdlib>
 #include <cuda.h>   // CUtensorMap + enums (types only: the encoder is resolved through cudaGetDriverEntryPoint)
 
 #include "warp_params.cuh"
 
 #ifndef LH_TMA_STAGES
-#define LH_TMA_STAGES 2
+#define LH_TMA_STAGES 3
 #endif
 #ifndef LH_TMA_MINB
-#define LH_TMA_MINB 8
+#define LH_TMA_MINB 6
+#endif
+#ifndef LH_TMA_CTAS
+#define LH_TMA_CTAS 4     // resident CTAs per SM the persistent grid is sized for (measured optimum)
 #endif
 
 namespace lh {
@@ -305,6 +309,7 @@ static bool make_maps(const MapKey& k, CUtensorMap* small, CUtensorMap* large) {
 template <int NORM, int GEO>
 static int launch_norm(const CUtensorMap& ms, const CUtensorMap& ml, const WarpParams& p, cudaStream_t st) {
     static int cap = 0;     // resident CTAs of this instantiation on the device model (B200); benign race: same value
+    static int sms_cached = 0;
     const size_t smem = 128 + (size_t)kStages * kStageBytes2 + 64 + (NORM == 2 ? 768 * sizeof(float) : 0);
     if (cap <= 0) {
         int dev = 0, sms = 0, occ = 0;
@@ -315,12 +320,23 @@ static int launch_norm(const CUtensorMap& ms, const CUtensorMap& ml, const WarpP
             return (int)cudaGetLastError();
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, warp_tma_kernel<NORM, GEO>, kTmaThreads, smem) != cudaSuccess)
             return (int)cudaGetLastError();
+        sms_cached = sms;
         cap = sms * (occ < 1 ? 1 : occ);
     }
     const int tiles_x = (p.ow + kTmaTile - 1) / kTmaTile, tiles_y = (p.oh + kTmaTile - 1) / kTmaTile;
     const long long total = (long long)tiles_x * tiles_y * p.N;
     if (total >= (1LL << 31)) return LH_EUNSUPPORTED;
-    const unsigned grid = (unsigned)(total < cap ? total : cap);
+    // FOUR CTAs per SM, not the eight that fit: measured on B200 (C2 / C3 / C5, 3 stages) 8: 49.0 / 38.8 / 99.1 us, 6: 48.0 / 37.2 / 96.1,
+    // 5: 45.7 / 36.2 / 90.0, 4: 43.9 / 35.2 / 87.2, 3: 48.5 / 38.8 / 88.4, 2: 57.2 / 44.4 / 102 -- the kernel is bound by its store
+    // stream, fewer tiles in flight keep it more sequential, and below 4 the 16 rendering warps per SM run out of issue slots.
+    // LH_K1_CTAS in the environment overrides it for such sweeps.
+    long long want = cap;
+    {
+        static const int env_ctas = [] { const char* e = getenv("LH_K1_CTAS"); return e ? atoi(e) : 0; }();
+        const long long per_sm = env_ctas > 0 ? env_ctas : LH_TMA_CTAS;
+        if (per_sm * sms_cached < want) want = per_sm * sms_cached;
+    }
+    const unsigned grid = (unsigned)(total < want ? total : want);
     warp_tma_kernel<NORM, GEO><<<grid, kTmaThreads, smem, st>>>(ms, ml, p, tiles_x, tiles_y, (int)total);
     return LH_OK;
 }
