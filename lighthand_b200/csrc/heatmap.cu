@@ -301,7 +301,10 @@ template <bool PRED, int TSRC, int FLAGS>
 __global__ void __launch_bounds__(kWarpThreads, TSRC == 2 ? 3 : LH_HM_MINB) heatmap_warp_kernel(const __grid_constant__ HeatmapParams p) {
     constexpr bool GRAD = (FLAGS & F_GRAD) != 0, TOUT = (FLAGS & F_TOUT) != 0, DEC = PRED && (FLAGS & F_DEC) != 0,
                    WGT = (FLAGS & F_WGT) != 0, LOSS = PRED && TSRC != 0;
-    constexpr int kU = (TSRC == 2) ? 2 : 4;        // float4 per buffer; two buffers (one in flight, one being consumed)
+#ifndef LH_HM_KU
+#define LH_HM_KU 4
+#endif
+    constexpr int kU = (TSRC == 2) ? LH_HM_KU / 2 : LH_HM_KU;   // float4 per buffer; two buffers (one in flight, one being consumed)
     __shared__ float s_tab[TSRC == 1 ? kMaxTable : 1];
     __shared__ double s_wl[kWarpsPerCta], s_we[kWarpsPerCta];
     __shared__ unsigned int s_ww[kWarpsPerCta];
