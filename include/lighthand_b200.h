@@ -401,6 +401,35 @@ int lh_pipeline_read_metrics(lh_pipeline* p, unsigned long long* counts4, double
 int lh_pipeline_reset_metrics(lh_pipeline* p);
 /* number of kernel launches one step issues (for accounting) */
 int lh_pipeline_launches_per_step(const lh_pipeline* p);
+/* ------------------------------------------------------------------------------------------
+ * Stage ring: stream / event plumbing of the pipelined DEVICE-resident form (what HeatmapPipeline.data_stage / loss_stage
+ * and PreparedStep.launch_data / launch_loss run on).  The ring owns a data stream and the events of two slots; the
+ * caller owns the two network-input buffers.  K1 of batch i+1 (data stream) then overlaps whatever the caller enqueues
+ * on its own stream for batch i (backbone, fused loss pass) -- the reference's loop shape (src/utils/method.py:160-183).
+ *   begin_data(slot, ...)  data stream waits for the inputs -- wait_mode 0: nothing (resident inputs), 1: `wait_event`
+ *                          (a cudaEvent_t), 2: everything enqueued so far on `after_stream` -- and for the slot's
+ *                          previous consumer;   end_data(slot) records "input ready"
+ *   begin_loss(slot, s)    stream s waits for "input ready";   end_loss(slot, s) records "slot consumed" on s
+ *   lh_stage_ring_data / lh_stage_ring_loss = begin + lh_warp_normalize / lh_heatmap_fused + end in ONE call
+ * ------------------------------------------------------------------------------------------ */
+typedef struct lh_warp_args {     /* the arguments of lh_warp_normalize */
+    const uint8_t* src; int64_t src_img_stride; int32_t src_h, src_w, src_pitch;
+    const double* fwd_affine; const uint8_t* flip; const double* chan_gain;
+    float mean_std[6]; int32_t has_mean_std;
+    const float* lut; int32_t interp, chan_order, out_layout;
+    float* dst; int32_t N, out_h, out_w;
+} lh_warp_args;
+typedef struct lh_stage_ring lh_stage_ring;
+int lh_stage_ring_create(int device, lh_stage_ring** out);
+void lh_stage_ring_destroy(lh_stage_ring* r);
+void* lh_stage_ring_data_stream(lh_stage_ring* r);   /* cudaStream_t */
+int lh_stage_ring_begin_data(lh_stage_ring* r, int slot, void* wait_event, void* after_stream, int wait_mode);
+int lh_stage_ring_end_data(lh_stage_ring* r, int slot);
+int lh_stage_ring_begin_loss(lh_stage_ring* r, int slot, lh_stream_t stream);
+int lh_stage_ring_end_loss(lh_stage_ring* r, int slot, lh_stream_t stream);
+int lh_stage_ring_data(lh_stage_ring* r, int slot, const lh_warp_args* a);
+int lh_stage_ring_loss(lh_stage_ring* r, int slot, const lh_heatmap_args* a, lh_stream_t stream);
+
 /* pinned host memory so the copies above run at full DMA rate */
 void* lh_host_alloc(size_t bytes);
 void lh_host_free(void* p);

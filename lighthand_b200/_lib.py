@@ -59,6 +59,15 @@ class PipelineIO(C.Structure):
     ]
 
 
+class WarpArgs(C.Structure):
+    _fields_ = [
+        ("src", c_p), ("src_img_stride", c_i64), ("src_h", C.c_int32), ("src_w", C.c_int32), ("src_pitch", C.c_int32),
+        ("fwd_affine", c_p), ("flip", c_p), ("chan_gain", c_p), ("mean_std", c_f * 6), ("has_mean_std", C.c_int32),
+        ("lut", c_p), ("interp", C.c_int32), ("chan_order", C.c_int32), ("out_layout", C.c_int32),
+        ("dst", c_p), ("N", C.c_int32), ("out_h", C.c_int32), ("out_w", C.c_int32),
+    ]
+
+
 class FreiDesc(C.Structure):
     _fields_ = [
         ("ulx", C.c_int32), ("uly", C.c_int32), ("cw", C.c_int32), ("ch", C.c_int32), ("pad", C.c_int32),
@@ -112,6 +121,15 @@ PROTOTYPES = {
     "lh_pipeline_read_metrics": (c_i, [c_p, c_p, c_p]),
     "lh_pipeline_reset_metrics": (c_i, [c_p]),
     "lh_pipeline_launches_per_step": (c_i, [c_p]),
+    "lh_stage_ring_create": (c_i, [c_i, C.POINTER(c_p)]),
+    "lh_stage_ring_destroy": (None, [c_p]),
+    "lh_stage_ring_data_stream": (c_p, [c_p]),
+    "lh_stage_ring_begin_data": (c_i, [c_p, c_i, c_p, c_p, c_i]),
+    "lh_stage_ring_end_data": (c_i, [c_p, c_i]),
+    "lh_stage_ring_begin_loss": (c_i, [c_p, c_i, c_p]),
+    "lh_stage_ring_end_loss": (c_i, [c_p, c_i, c_p]),
+    "lh_stage_ring_data": (c_i, [c_p, c_i, C.POINTER(WarpArgs)]),
+    "lh_stage_ring_loss": (c_i, [c_p, c_i, C.POINTER(HeatmapArgs), c_p]),
     "lh_host_alloc": (c_p, [C.c_size_t]),
     "lh_host_free": (None, [c_p]),
     "lh_jpeg_create": (c_i, [c_i, c_i, c_i, C.POINTER(c_p)]),

@@ -331,6 +331,111 @@ extern "C" int lh_pipeline_step_host(lh_pipeline* p, const lh_pipeline_io* io) {
     return lh_pipeline_wait(p, si);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stage ring: the stream / event plumbing of the pipelined DEVICE-resident form (HeatmapPipeline.data_stage / loss_stage,
+// PreparedStep.launch_data / launch_loss) in C, so that one step costs two library calls and no per-step Python stream or
+// event work -- at ~90 us per step eight ranks sharing a host could not keep their GPUs fed through torch's wrappers.
+// Two slots (network-input buffers owned by the caller); a data stream owned by the ring.
+// ------------------------------------------------------------------------------------------------
+struct lh_stage_ring {
+    int device = 0;
+    cudaStream_t s_data = nullptr;
+    cudaEvent_t ev_ready[kSlots] = {nullptr, nullptr};   // K1 of the slot finished (recorded on the data stream)
+    cudaEvent_t ev_free[kSlots] = {nullptr, nullptr};    // the slot's consumer finished (recorded on the caller's stream)
+    cudaEvent_t ev_in = nullptr;                         // "inputs produced so far on the caller's stream"
+    bool free_valid[kSlots] = {false, false};
+};
+
+extern "C" void lh_stage_ring_destroy(lh_stage_ring* r) {
+    if (!r) return;
+    cudaSetDevice(r->device);
+    if (r->s_data) cudaStreamSynchronize(r->s_data);
+    for (int i = 0; i < kSlots; ++i) {
+        if (r->ev_ready[i]) cudaEventDestroy(r->ev_ready[i]);
+        if (r->ev_free[i]) cudaEventDestroy(r->ev_free[i]);
+    }
+    if (r->ev_in) cudaEventDestroy(r->ev_in);
+    if (r->s_data) cudaStreamDestroy(r->s_data);
+    delete r;
+}
+
+extern "C" int lh_stage_ring_create(int device, lh_stage_ring** out) {
+    if (!out) return LH_ENULL;
+    int rc = LH_OK;
+    lh_stage_ring* r = new (std::nothrow) lh_stage_ring();
+    if (!r) return LH_ENOMEM;
+    r->device = device;
+    PCHK(cudaSetDevice(device));
+    PCHK(cudaStreamCreateWithFlags(&r->s_data, cudaStreamNonBlocking));
+    for (int i = 0; i < kSlots; ++i) {
+        PCHK(cudaEventCreateWithFlags(&r->ev_ready[i], cudaEventDisableTiming));
+        PCHK(cudaEventCreateWithFlags(&r->ev_free[i], cudaEventDisableTiming));
+    }
+    PCHK(cudaEventCreateWithFlags(&r->ev_in, cudaEventDisableTiming));
+    *out = r;
+    return LH_OK;
+fail:
+    lh_stage_ring_destroy(r);
+    return rc;
+}
+
+extern "C" void* lh_stage_ring_data_stream(lh_stage_ring* r) { return r ? (void*)r->s_data : nullptr; }
+
+// data stream: wait for the inputs (an event, or everything enqueued so far on `after_stream`, or nothing) and for the
+// previous consumer of the slot's input buffer
+extern "C" int lh_stage_ring_begin_data(lh_stage_ring* r, int slot, void* wait_event, void* after_stream, int wait_mode) {
+    if (!r) return LH_ENULL;
+    if (slot < 0 || slot >= kSlots || wait_mode < 0 || wait_mode > 2) return LH_EINVAL;
+    cudaError_t e = cudaSuccess;
+    if (wait_mode == 1) {                     // an event the caller recorded
+        if (!wait_event) return LH_ENULL;
+        e = cudaStreamWaitEvent(r->s_data, (cudaEvent_t)wait_event, 0);
+    } else if (wait_mode == 2) {              // everything enqueued so far on the caller's stream
+        e = cudaEventRecord(r->ev_in, (cudaStream_t)after_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(r->s_data, r->ev_in, 0);
+    }
+    if (e == cudaSuccess && r->free_valid[slot]) e = cudaStreamWaitEvent(r->s_data, r->ev_free[slot], 0);
+    return (int)e;
+}
+extern "C" int lh_stage_ring_end_data(lh_stage_ring* r, int slot) {
+    if (!r) return LH_ENULL;
+    if (slot < 0 || slot >= kSlots) return LH_EINVAL;
+    return (int)cudaEventRecord(r->ev_ready[slot], r->s_data);
+}
+// caller's stream: wait for the slot's K1 (the backbone may read the slot's input from here on)
+extern "C" int lh_stage_ring_begin_loss(lh_stage_ring* r, int slot, lh_stream_t stream) {
+    if (!r) return LH_ENULL;
+    if (slot < 0 || slot >= kSlots) return LH_EINVAL;
+    return (int)cudaStreamWaitEvent((cudaStream_t)stream, r->ev_ready[slot], 0);
+}
+extern "C" int lh_stage_ring_end_loss(lh_stage_ring* r, int slot, lh_stream_t stream) {
+    if (!r) return LH_ENULL;
+    if (slot < 0 || slot >= kSlots) return LH_EINVAL;
+    const cudaError_t e = cudaEventRecord(r->ev_free[slot], (cudaStream_t)stream);
+    if (e == cudaSuccess) r->free_valid[slot] = true;
+    return (int)e;
+}
+
+// the two stages as ONE call each (resident inputs: nothing to wait for but the slot's previous consumer)
+extern "C" int lh_stage_ring_data(lh_stage_ring* r, int slot, const lh_warp_args* a) {
+    if (!r || !a) return LH_ENULL;
+    int rc = lh_stage_ring_begin_data(r, slot, nullptr, nullptr, 0);
+    if (rc) return rc;
+    rc = lh_warp_normalize(a->src, a->src_img_stride, a->src_h, a->src_w, a->src_pitch, a->fwd_affine, a->flip, a->chan_gain,
+                           a->has_mean_std ? a->mean_std : nullptr, a->lut, a->interp, a->chan_order, a->out_layout, a->dst,
+                           a->N, a->out_h, a->out_w, r->s_data);
+    if (rc) return rc;
+    return lh_stage_ring_end_data(r, slot);
+}
+extern "C" int lh_stage_ring_loss(lh_stage_ring* r, int slot, const lh_heatmap_args* a, lh_stream_t stream) {
+    if (!r || !a) return LH_ENULL;
+    int rc = lh_stage_ring_begin_loss(r, slot, stream);
+    if (rc) return rc;
+    rc = lh_heatmap_fused(a, stream);
+    if (rc) return rc;
+    return lh_stage_ring_end_loss(r, slot, stream);
+}
+
 // pinned host allocations for callers that want full-rate DMA into the pipeline
 extern "C" void* lh_host_alloc(size_t bytes) {
     void* q = nullptr;

@@ -52,9 +52,8 @@ class HeatmapPipeline:
         # batch i+1 never overwrites what the backbone of batch i is still reading
         self.inputs = [torch.empty((n, 3, *self.out_hw), dtype=f32, device=d) for _ in range(2)]
         self.input = self.inputs[0]
-        self._dstream = None            # data stream + events of the overlapped form (created on first use)
-        self._ev_k1 = self._ev_free = None
-        self._free_valid = [False, False]
+        self._dstream = None            # the C stage ring (data stream + slot events) of the pipelined form, created on first use
+        self._ring_h = None
         self._next_slot = 0
         self._pending = []
         self.buffers = {
@@ -121,41 +120,49 @@ class HeatmapPipeline:
         return out
 
     # -- the same step as a two-stage software pipeline ---------------------------------------------
-    def _overlap_state(self):
+    # Streams and events live in the C library (lh_stage_ring_*): a step costs two library calls and no per-step torch
+    # stream / event work.
+    def _ring(self):
         if self._dstream is None:
-            self._dstream = torch.cuda.Stream(self.device)
-            self._ev_k1 = [torch.cuda.Event(), torch.cuda.Event()]
-            self._ev_free = [torch.cuda.Event(), torch.cuda.Event()]
-        return self._dstream
+            lib = _lib.load()
+            h = C.c_void_p()
+            check(lib.lh_stage_ring_create(self.device.index, C.byref(h)), "lh_stage_ring_create")
+            self._ring_h, self._ring_lib = h, lib
+            self._dstream = torch.cuda.ExternalStream(int(lib.lh_stage_ring_data_stream(h)), device=self.device)
+        return self._ring_h
 
-    def _data_begin(self, wait_for) -> int:
-        """Stream bookkeeping shared by ``data_stage`` and ``PreparedStep.launch_data``: pick the slot and make the data
-        stream wait for the inputs' producer and for the previous consumer of the slot's input buffer."""
-        d = self._overlap_state()
+    def __del__(self):
+        h = getattr(self, "_ring_h", None)
+        if h:
+            self._ring_lib.lh_stage_ring_destroy(h)
+            self._ring_h = None
+
+    def _take_slot(self) -> int:
         slot = self._next_slot
         self._next_slot ^= 1
-        if wait_for is None:                 # inputs were produced on the caller's stream so far
-            wait_for = torch.cuda.Event()
-            wait_for.record(torch.cuda.current_stream(self.device))
-        if wait_for is not False:
-            d.wait_event(wait_for)
-        if self._free_valid[slot]:
-            d.wait_event(self._ev_free[slot])
         return slot
 
     def data_stage(self, images_u8: torch.Tensor, fwd_affine: Optional[torch.Tensor], flip: Optional[torch.Tensor] = None,
                    wait_for=None) -> torch.Tensor:
-        """Data stage of the NEXT batch: K1 on the internal data stream into the next input slot.  ``wait_for``: a
+        """Data stage of the NEXT batch: K1 on the ring's data stream into the next input slot.  ``wait_for``: a
         torch.cuda.Event after which the images are valid (default: everything enqueued so far on the current stream;
         ``False``: nothing to wait for -- resident inputs).  Returns the slot's input tensor; it is valid on the current
         stream once ``loss_stage`` (or ``input_ready``) for this batch has been called."""
         if images_u8.shape[0] != self.N:
             raise LighthandError("HeatmapPipeline.data_stage: batch size differs from the one the pipeline was built for")
-        slot = self._data_begin(wait_for)
+        r, lib = self._ring(), _lib.load()
+        slot = self._take_slot()
+        if wait_for is False:
+            check(lib.lh_stage_ring_begin_data(r, slot, None, None, 0), "lh_stage_ring_begin_data")
+        elif wait_for is None:
+            check(lib.lh_stage_ring_begin_data(r, slot, None, torch.cuda.current_stream(self.device).cuda_stream, 2),
+                  "lh_stage_ring_begin_data")
+        else:
+            check(lib.lh_stage_ring_begin_data(r, slot, wait_for.cuda_event, None, 1), "lh_stage_ring_begin_data")
         with torch.cuda.stream(self._dstream):
             ops.warp_normalize(images_u8, fwd_affine, self.out_hw, flip=flip, mean=self.mean, std=self.std,
                                lut=self.lut, interp=self.interp, out=self.inputs[slot], exact_norm=self.exact_norm)
-        self._ev_k1[slot].record(self._dstream)
+        check(lib.lh_stage_ring_end_data(r, slot), "lh_stage_ring_end_data")
         self._pending.append(slot)
         return self.inputs[slot]
 
@@ -165,14 +172,9 @@ class HeatmapPipeline:
         if not self._pending:
             raise LighthandError("HeatmapPipeline.input_ready: no data stage pending")
         slot = self._pending[0]
-        torch.cuda.current_stream(self.device).wait_event(self._ev_k1[slot])
+        check(self._ring_lib.lh_stage_ring_begin_loss(self._ring_h, slot, torch.cuda.current_stream(self.device).cuda_stream),
+              "lh_stage_ring_begin_loss")
         return self.inputs[slot]
-
-    def _loss_end(self) -> int:
-        slot = self._pending.pop(0)
-        self._ev_free[slot].record(torch.cuda.current_stream(self.device))
-        self._free_valid[slot] = True
-        return slot
 
     def loss_stage(self, pred: torch.Tensor, joints: torch.Tensor, inv_affine: Optional[torch.Tensor] = None) -> dict:
         """Loss stage of the CURRENT batch (the oldest pending data stage) on the current stream: waits for its K1,
@@ -184,7 +186,9 @@ class HeatmapPipeline:
                           inv_affine=inv_affine if self.map_back else None,
                           loss_meter=self.meter.loss_meter, buffers=self.buffers,
                           metrics=(self.meter.counts, self.meter.sums), pck_T=self.pck_T, use_vis=self.use_vis)
-        self._loss_end()
+        slot = self._pending.pop(0)
+        check(self._ring_lib.lh_stage_ring_end_loss(self._ring_h, slot, torch.cuda.current_stream(self.device).cuda_stream),
+              "lh_stage_ring_end_loss")
         out = dict(self.buffers)
         out["input"] = inp
         out.pop("ws")
@@ -258,6 +262,20 @@ class PreparedStep:
                       ptr(p.lut), p.interp, ops.LH_CHAN_RGB, ops.LH_LAYOUT_CHW, inp.data_ptr(), n, p.out_hw[0], p.out_hw[1])
                      for inp in p.inputs]
         self._k1 = self._k1s[0]
+        self._wargs, self._wrefs = [], []
+        for inp in p.inputs:                       # the same K1 call as an lh_warp_args record, one per input slot
+            w = _lib.WarpArgs()
+            w.src, w.src_img_stride, w.src_h, w.src_w, w.src_pitch = images_u8.data_ptr(), sh * sw * 3, sh, sw, sw * 3
+            w.fwd_affine, w.flip, w.chan_gain = ptr(fwd_affine), ptr(flip), None
+            w.has_mean_std = int(self._ms is not None)
+            if self._ms is not None:
+                for i in range(6):
+                    w.mean_std[i] = self._ms[i]
+            w.lut, w.interp, w.chan_order, w.out_layout = ptr(p.lut), p.interp, ops.LH_CHAN_RGB, ops.LH_LAYOUT_CHW
+            w.dst, w.N, w.out_h, w.out_w = inp.data_ptr(), n, p.out_hw[0], p.out_hw[1]
+            self._wargs.append(w)
+            self._wrefs.append(C.byref(w))
+        self._ring_data, self._ring_loss = lib.lh_stage_ring_data, lib.lh_stage_ring_loss
         a = _lib.HeatmapArgs()
         b = p.buffers
         table, side = ops.hrnet_table(p.sigma, p.device)
@@ -296,24 +314,24 @@ class PreparedStep:
             check(rc, "prepared step")
 
     def launch_data(self) -> None:
-        """Overlapped form, data stage: K1 of THIS prepared batch on the pipeline's data stream (resident inputs:
-        nothing to wait for except the slot's previous consumer)."""
+        """Pipelined form, data stage: K1 of THIS prepared batch on the ring's data stream (resident inputs: nothing to
+        wait for except the slot's previous consumer).  One library call."""
         p = self._keep[6]
-        slot = p._data_begin(False)
-        rc = self._f1(*self._k1s[slot], p._dstream.cuda_stream)
+        r = p._ring()
+        slot = p._take_slot()
+        rc = self._ring_data(r, slot, self._wrefs[slot])
         if rc:
             check(rc, "prepared step (data stage)")
-        p._ev_k1[slot].record(p._dstream)
         p._pending.append(slot)
 
     def launch_loss(self) -> None:
-        """Overlapped form, loss stage of THIS prepared batch on the current stream (after its ``launch_data``)."""
+        """Pipelined form, loss stage of THIS prepared batch on the current stream (after its ``launch_data``).  One
+        library call."""
         p = self._keep[6]
-        p.input_ready()
-        rc = self._f2(self._aref, torch.cuda.current_stream().cuda_stream)
+        slot = p._pending.pop(0)
+        rc = self._ring_loss(p._ring_h, slot, self._aref, torch.cuda.current_stream().cuda_stream)
         if rc:
             check(rc, "prepared step (loss stage)")
-        p._loss_end()
 
     def launch_split(self, stream_k1: int, stream_fused: int) -> None:
         """K1 and the fused heat-map pass touch disjoint data (images -> input; pred/joints -> grad/coords), so
