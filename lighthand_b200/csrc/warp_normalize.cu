@@ -902,8 +902,12 @@ extern "C" int lh_warp_normalize(const uint8_t* src, int64_t src_img_stride, int
                 q.mean[i] = (float)(1.0 / (255.0 * sd));
                 q.stdv[i] = (float)(-mu / sd);
             }
-            dim3 fgrid((out_w + kTileW - 1) / kTileW, (out_h + kTileH - 1) / kTileH, N);
-            resize_pairs_kernel<<<fgrid, kFThreads, 0, st>>>(q);
+            int rc_t = k1_force_records() ? kTmaNotApplicable : launch_resize_tma(q, st);
+            if (rc_t != LH_OK && rc_t != kTmaNotApplicable) return rc_t;
+            if (rc_t == kTmaNotApplicable) {
+                dim3 fgrid((out_w + kTileW - 1) / kTileW, (out_h + kTileH - 1) / kTileH, N);
+                resize_pairs_kernel<<<fgrid, kFThreads, 0, st>>>(q);
+            }
         } else {
             resize_torch_kernel<<<grid, block, 0, st>>>(p);
         }

@@ -26,5 +26,7 @@ struct WarpParams {
 // anything else is an error.  `norm`: 0 raw 0..255, 1 one FMA (p.mean = a, p.stdv = b), 2 table (p.lut).
 constexpr int kTmaNotApplicable = 0x7fff0001;
 int launch_warp_tma(const WarpParams& p, int norm, cudaStream_t st);
+// LH_INTERP_TORCH (ToTensor -> Resize -> Normalize) on the same TMA ring; p.mean / p.stdv hold a, b of v * a + b (byte units)
+int launch_resize_tma(const WarpParams& p, cudaStream_t st);
 
 }  // namespace lh

@@ -42,9 +42,11 @@ constexpr int kConsWarps = 4;
 constexpr int kTmaThreads = 32 * (kConsWarps + 1);
 constexpr int kTmaTile = 32;               // output tile: 32 x 32
 constexpr int kRawBytes = kBoxW * kBoxHL;  // 7680
-// stage = raw bytes | ad[32] bd[32] x0[32] y0[32] | StageInfo; a tap may read two words past its row: they land in the tables
+// stage = raw bytes | 5 tables of 32 words (warp: ad bd x0 y0 -; resize: cx lx1 r0 r1 ly1) | StageInfo; a tap may read two words
+// past its row: they land in the tables
 struct __align__(16) StageInfo { int lox, hix, loy, hiy, flags, n, tx0, ty0, base, pad0, pad1, pad2; };
-constexpr int kStageBytes2 = ((kRawBytes + 4 * 32 * 4 + (int)sizeof(StageInfo)) + 127) & ~127;   // 8320
+constexpr int kTabWords = 5 * 32;
+constexpr int kStageBytes2 = ((kRawBytes + kTabWords * 4 + (int)sizeof(StageInfo)) + 127) & ~127;   // 8448
 static_assert(kRawBytes % 128 == 0, "TMA destinations must stay 128-byte aligned");
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
@@ -231,7 +233,7 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tm_small, const __grid_const
             int* tab = reinterpret_cast<int*>(stage + kRawBytes);
             mbar_wait(smem_u32(s_bar + kStages + s), ph);            // the consumers are done with this stage
             tab[lane] = ad; tab[32 + lane] = bd; tab[64 + lane] = x0; tab[96 + lane] = y0;
-            if (lane == 0) *reinterpret_cast<StageInfo*>(tab + 128) = inf;
+            if (lane == 0) *reinterpret_cast<StageInfo*>(tab + kTabWords) = inf;
             __syncwarp();
             if (lane == 0) {
                 const uint32_t full = smem_u32(s_bar + s);
@@ -253,9 +255,166 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tm_small, const __grid_const
             const uint8_t* stage = s_base + s * kStageBytes2;
             const int* tab = reinterpret_cast<const int*>(stage + kRawBytes);
             mbar_wait(smem_u32(s_bar + s), ph);
-            const StageInfo inf = *reinterpret_cast<const StageInfo*>(tab + 128);   // 16-byte aligned: 3 x LDS.128
+            const StageInfo inf = *reinterpret_cast<const StageInfo*>(tab + kTabWords);   // 16-byte aligned: 3 x LDS.128
             if (inf.flags & 1) render_rows<NORM, GEO, true>(p, inf, stage, tab, s_lut, lane, warp);
             else               render_rows<NORM, GEO, false>(p, inf, stage, tab, s_lut, lane, warp);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(s_bar + kStages + s));
+            if (++s == kStages) { s = 0; ph ^= 1u; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LH_INTERP_TORCH on the same ring: ToTensor -> Resize(bilinear, align_corners=False, no antialias) -> Normalize
+// (src/tools/dataset.py:147-157, the LightHand99K dataset path).  Producer: torch's source index / lambda per output column
+// and row of the tile (float32, ATen's fused scale * (dst + 0.5) - 0.5), the tile's source window, one TMA load.  Consumers
+// (lane = output column, 8 rows per warp) interpolate each needed SOURCE row horizontally ONCE -- H(y) = lx0 p(y,x0) +
+// lx1 p(y,x1) per channel, from the raw bytes: 3 LDS + 2 funnel shifts + 7 PRMT + 6 FADD -- and roll (H(y0), H(y1)) down the
+// output rows: up-sampling 224 -> 256 needs 1.14 horizontal passes per output pixel instead of 2, i.e. 6.9 byte->float
+// conversions instead of 12 (the record-staging kernel resize_pairs_kernel is bound by exactly those).  Same float operations as
+// resize_pairs_kernel (value in byte units, one FMA normalises): identical results.  Right / bottom edge: torch clamps the
+// second tap to the last pixel; here the lane's PRMT selector repeats the first tap's bytes / the row table repeats the row.
+// ------------------------------------------------------------------------------------------------
+template <int GEO>
+__global__ void __launch_bounds__(kTmaThreads, LH_TMA_MINB)
+resize_tma_kernel(const __grid_constant__ CUtensorMap tm_small, const __grid_constant__ CUtensorMap tm_large,
+                  const WarpParams p, int tiles_x, int tiles_y, int total_tiles) {
+    extern __shared__ uint8_t s_dyn[];
+    uint8_t* s_base = s_dyn + ((128u - (smem_u32(s_dyn) & 127u)) & 127u);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_base + kStages * kStageBytes2);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(smem_u32(s_bar + s), 1);
+            mbar_init(smem_u32(s_bar + kStages + s), kConsWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int ow = GEO ? GEO : p.ow, oh = GEO ? GEO : p.oh;
+
+    if (warp == kConsWarps) {
+        // ---------------- producer ----------------
+        const float sy = __fdiv_rn((float)p.sh, (float)oh), sx = __fdiv_rn((float)p.sw, (float)ow);
+        auto src_index = [](float scale, int d) {
+            const float f = fmaf(scale, __fadd_rn((float)d, 0.5f), -0.5f);
+            return f < 0.f ? 0.f : f;
+        };
+        const int tiles_img = tiles_x * tiles_y;
+        int s = 0;
+        uint32_t ph = 1;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int n = t / tiles_img, r = t - n * tiles_img;
+            const int ty = r / tiles_x, tx = r - ty * tiles_x;
+            const int tx0 = tx * kTmaTile, ty0 = ty * kTmaTile;
+            const int cl = min(kTmaTile, ow - tx0) - 1, rl = min(kTmaTile, oh - ty0) - 1;
+            const float fx = src_index(sx, tx0 + min(lane, cl));
+            const int x0 = min((int)fx, p.sw - 1);
+            const float lx1 = fminf(fmaxf(__fsub_rn(fx, (float)x0), 0.f), 1.f);
+            const float fy = src_index(sy, ty0 + min(lane, rl));
+            const int y0 = min((int)fy, p.sh - 1), y1 = min(y0 + 1, p.sh - 1);
+            const float ly1 = fminf(fmaxf(__fsub_rn(fy, (float)y0), 0.f), 1.f);
+            StageInfo inf;
+            inf.lox = __shfl_sync(0xffffffffu, x0, 0); inf.hix = __shfl_sync(0xffffffffu, x0, cl);     // window columns lox .. hix + 1
+            inf.loy = __shfl_sync(0xffffffffu, y0, 0); inf.hiy = __shfl_sync(0xffffffffu, y1, rl);     // window rows loy .. hiy
+            const int c0 = (3 * inf.lox) & ~15;
+            const int nrows = inf.hiy - inf.loy + 1;
+            inf.flags = 1; inf.n = n; inf.tx0 = tx0; inf.ty0 = ty0;
+            inf.base = -inf.loy * kBoxW - c0;
+            inf.pad0 = inf.pad1 = inf.pad2 = 0;
+            uint8_t* stage = s_base + s * kStageBytes2;
+            int* tab = reinterpret_cast<int*>(stage + kRawBytes);
+            mbar_wait(smem_u32(s_bar + kStages + s), ph);
+            tab[lane] = 3 * x0; tab[32 + lane] = __float_as_int(lx1);
+            tab[64 + lane] = y0; tab[96 + lane] = y1; tab[128 + lane] = __float_as_int(ly1);
+            if (lane == 0) *reinterpret_cast<StageInfo*>(tab + kTabWords) = inf;
+            __syncwarp();
+            if (lane == 0) {
+                const uint32_t full = smem_u32(s_bar + s);
+                const bool small = nrows <= kBoxHS;
+                mbar_expect_tx(full, (uint32_t)(kBoxW * (small ? kBoxHS : kBoxHL)));
+                tma_load_3d(smem_u32(stage), small ? &tm_small : &tm_large, full, c0, inf.loy, n);
+            }
+            if (++s == kStages) { s = 0; ph ^= 1u; }
+        }
+    } else {
+        // ---------------- consumers ----------------
+        const float na0 = p.mean[0], na1 = p.mean[1], na2 = p.mean[2];   // a, b of v * a + b (v in byte units)
+        const float nb0 = p.stdv[0], nb1 = p.stdv[1], nb2 = p.stdv[2];
+        int s = 0;
+        uint32_t ph = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const uint8_t* stage = s_base + s * kStageBytes2;
+            const int* tab = reinterpret_cast<const int*>(stage + kRawBytes);
+            mbar_wait(smem_u32(s_bar + s), ph);
+            const StageInfo inf = *reinterpret_cast<const StageInfo*>(tab + kTabWords);
+            const int ox = inf.tx0 + lane, r0 = warp * 8, oy = inf.ty0 + r0;
+            if (GEO || (ox < ow && oy < oh)) {
+                const int cx = tab[lane];
+                const float lx1 = __int_as_float(tab[32 + lane]), lx0 = __fsub_rn(1.0f, lx1);
+                // second tap = the next pixel's bytes 3..5 of the window, or the first tap again at the right edge (torch's clamp)
+                const uint32_t sel1 = (cx == 3 * (p.sw - 1)) ? 0x3210u : 0x6543u;
+                const uint32_t org = smem_u32(stage) + (uint32_t)inf.base + (uint32_t)cx;
+                const int rows = GEO ? 8 : min(8, oh - oy);
+                float* d0 = nullptr;
+                unsigned i0 = 0, i1 = 0, i2 = 0, step = 0;
+                if (GEO) {
+                    d0 = p.dst + (((size_t)inf.n * 3 * GEO + oy) * GEO + ox);
+                } else {
+                    if (p.layout == LH_LAYOUT_CHW) {
+                        const unsigned plane = (unsigned)(oh * ow);
+                        i0 = ((unsigned)(inf.n * 3) * oh + oy) * ow + ox;
+                        i1 = i0 + plane; i2 = i1 + plane;
+                        step = (unsigned)ow;
+                    } else {
+                        i0 = (((unsigned)inf.n * oh + oy) * ow + ox) * 3u;
+                        i1 = i0 + 1; i2 = i0 + 2;
+                        step = 3u * (unsigned)ow;
+                    }
+                    if (p.chan_order == LH_CHAN_BGR) { const unsigned tt = i0; i0 = i2; i2 = tt; }
+                }
+                // horizontally interpolated source row y (byte units), all three channels
+                auto hrow = [&](int y, float& hr, float& hg, float& hb) {
+                    const uint32_t o = (uint32_t)(y * kBoxW) + org;
+                    const uint32_t* q = reinterpret_cast<const uint32_t*>(__cvta_shared_to_generic(o & ~3u));
+                    const uint32_t sh = o << 3;
+                    const uint32_t a = q[0], b = q[1], c = q[2];
+                    const uint32_t lo = __funnelshift_r(a, b, sh), hi = __funnelshift_r(b, c, sh);   // R0 G0 B0 R1 | G1 B1 - -
+                    const uint32_t t1 = __byte_perm(lo, hi, sel1);                                   // R1 G1 B1 -  (or R0 G0 B0 -)
+                    auto bytef = [](uint32_t w, uint32_t k) {   // byte k of w as float without I2F: under the exponent of 2^23
+                        return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u | k)) - 8388608.0f;
+                    };
+                    hr = fmaf(lx1, bytef(t1, 0), lx0 * bytef(lo, 0));
+                    hg = fmaf(lx1, bytef(t1, 1), lx0 * bytef(lo, 1));
+                    hb = fmaf(lx1, bytef(t1, 2), lx0 * bytef(lo, 2));
+                };
+                int cur_lo = -1, cur_hi = -1;
+                float lr = 0.f, lg = 0.f, lb = 0.f, hr = 0.f, hg = 0.f, hb = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (!GEO && j >= rows) break;
+                    const int y0 = tab[64 + r0 + j], y1 = tab[96 + r0 + j];        // warp-uniform
+                    const float ly1 = __int_as_float(tab[128 + r0 + j]), ly0 = __fsub_rn(1.0f, ly1);
+                    if (y0 != cur_lo) {
+                        if (y0 == cur_hi) { lr = hr; lg = hg; lb = hb; } else hrow(y0, lr, lg, lb);
+                        cur_lo = y0;
+                    }
+                    if (y1 != cur_hi) {
+                        if (y1 == cur_lo) { hr = lr; hg = lg; hb = lb; } else hrow(y1, hr, hg, hb);
+                        cur_hi = y1;
+                    }
+                    const float vr = fmaf(ly1, hr, ly0 * lr), vg = fmaf(ly1, hg, ly0 * lg), vb = fmaf(ly1, hb, ly0 * lb);
+                    const float o0 = fmaf(vr, na0, nb0), o1 = fmaf(vg, na1, nb1), o2 = fmaf(vb, na2, nb2);
+                    if (GEO) {
+                        __stcs(d0 + j * GEO, o0); __stcs(d0 + GEO * GEO + j * GEO, o1); __stcs(d0 + 2 * GEO * GEO + j * GEO, o2);
+                    } else {
+                        __stcs(p.dst + i0, o0); __stcs(p.dst + i1, o1); __stcs(p.dst + i2, o2);
+                        i0 += step; i1 += step; i2 += step;
+                    }
+                }
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(s_bar + kStages + s));
             if (++s == kStages) { s = 0; ph ^= 1u; }
@@ -351,24 +510,60 @@ static int launch_geo(const CUtensorMap& ms, const CUtensorMap& ml, const WarpPa
     return launch_norm<NORM, 0>(ms, ml, p, st);
 }
 
+template <int GEO>
+static int launch_resize_geo(const CUtensorMap& ms, const CUtensorMap& ml, const WarpParams& p, cudaStream_t st) {
+    static int cap = 0, sms_cached = 0;
+    const size_t smem = 128 + (size_t)kStages * kStageBytes2 + 64;
+    if (cap <= 0) {
+        int dev = 0, sms = 0, occ = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return (int)cudaGetLastError();
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return (int)cudaGetLastError();
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resize_tma_kernel<GEO>, kTmaThreads, smem) != cudaSuccess)
+            return (int)cudaGetLastError();
+        sms_cached = sms;
+        cap = sms * (occ < 1 ? 1 : occ);
+    }
+    const int tiles_x = (p.ow + kTmaTile - 1) / kTmaTile, tiles_y = (p.oh + kTmaTile - 1) / kTmaTile;
+    const long long total = (long long)tiles_x * tiles_y * p.N;
+    if (total >= (1LL << 31)) return LH_EUNSUPPORTED;
+    long long want = cap;
+    {
+        static const int env_ctas = [] { const char* e = getenv("LH_K1_CTAS"); return e ? atoi(e) : 0; }();
+        const long long per_sm = env_ctas > 0 ? env_ctas : LH_TMA_CTAS;
+        if (per_sm * sms_cached < want) want = per_sm * sms_cached;
+    }
+    const unsigned grid = (unsigned)(total < want ? total : want);
+    resize_tma_kernel<GEO><<<grid, kTmaThreads, smem, st>>>(ms, ml, p, tiles_x, tiles_y, (int)total);
+    return LH_OK;
+}
+
+static const struct MapEntry* lookup_maps(const WarpParams& p);
+
+// LH_INTERP_TORCH through the ring (p.mean / p.stdv = a, b of v * a + b in byte units).  kTmaNotApplicable: alignment, flip /
+// gain, or a source window that does not fit the box (down-sampling by more than ~1.4) -- the caller keeps its other kernels.
+int launch_resize_tma(const WarpParams& p, cudaStream_t st) {
+    if (((reinterpret_cast<uintptr_t>(p.src) | (uintptr_t)p.pitch | (uintptr_t)p.img_stride) & 15u) != 0) return kTmaNotApplicable;
+    if (p.flip || p.gain) return kTmaNotApplicable;
+    // window of a 32 x 32 output tile: columns 32 * sw / ow + 2 (x 3 bytes, + 15 of box alignment), rows 32 * sh / oh + 2
+    if (3.0 * (32.0 * p.sw / p.ow + 3.0) + 15.0 > kBoxW || 32.0 * p.sh / p.oh + 3.0 > kBoxHL) return kTmaNotApplicable;
+    const MapEntry* e = lookup_maps(p);
+    if (!e) return kTmaNotApplicable;
+    const bool plain = p.layout == LH_LAYOUT_CHW && p.chan_order == LH_CHAN_RGB && p.oh == p.ow;
+    int rc;
+    if (plain && p.ow == 256)      rc = launch_resize_geo<256>(e->small, e->large, p, st);
+    else if (plain && p.ow == 224) rc = launch_resize_geo<224>(e->small, e->large, p, st);
+    else                           rc = launch_resize_geo<0>(e->small, e->large, p, st);
+    if (rc) return rc;
+    LH_CHECK_LAUNCH();
+    return LH_OK;
+}
+
 int launch_warp_tma(const WarpParams& p, int norm, cudaStream_t st) {
     // what a tiled tensor map can describe: 16-byte aligned base and strides
     if (((reinterpret_cast<uintptr_t>(p.src) | (uintptr_t)p.pitch | (uintptr_t)p.img_stride) & 15u) != 0) return kTmaNotApplicable;
     if (p.gain || p.lut_per_image) return kTmaNotApplicable;      // per-image tables stay on the record kernel
-    const MapKey key{p.src, p.img_stride, p.N, p.sh, p.sw, p.pitch};
-    constexpr int kCache = 8;
-    thread_local MapEntry cache[kCache];
-    thread_local int next = 0;
-    const MapEntry* e = nullptr;
-    for (int i = 0; i < kCache; ++i) if (cache[i].valid && cache[i].key == key) { e = &cache[i]; break; }
-    if (!e) {
-        MapEntry& slot = cache[next];
-        next = (next + 1) % kCache;
-        slot.valid = false;
-        if (!make_maps(key, &slot.small, &slot.large)) return kTmaNotApplicable;
-        slot.key = key; slot.valid = true;
-        e = &slot;
-    }
+    const MapEntry* e = lookup_maps(p);
+    if (!e) return kTmaNotApplicable;
     int rc;
     if (norm == 2)      rc = launch_geo<2>(e->small, e->large, p, st);
     else if (norm == 1) rc = launch_geo<1>(e->small, e->large, p, st);
@@ -376,6 +571,21 @@ int launch_warp_tma(const WarpParams& p, int norm, cudaStream_t st) {
     if (rc) return rc;
     LH_CHECK_LAUNCH();
     return LH_OK;
+}
+
+// tensor maps of this source batch (thread-local cache: a training loop presents the same few buffers again and again)
+static const MapEntry* lookup_maps(const WarpParams& p) {
+    const MapKey key{p.src, p.img_stride, p.N, p.sh, p.sw, p.pitch};
+    constexpr int kCache = 8;
+    thread_local MapEntry cache[kCache];
+    thread_local int next = 0;
+    for (int i = 0; i < kCache; ++i) if (cache[i].valid && cache[i].key == key) return &cache[i];
+    MapEntry& slot = cache[next];
+    next = (next + 1) % kCache;
+    slot.valid = false;
+    if (!make_maps(key, &slot.small, &slot.large)) return nullptr;
+    slot.key = key; slot.valid = true;
+    return &slot;
 }
 
 }  // namespace lh

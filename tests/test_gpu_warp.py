@@ -163,6 +163,9 @@ for S, n in ((256, 7), (224, 2), (512, 3)):
     for tag, kw in (("lut", dict(exact_norm=True)), ("fma", dict(exact_norm=False)), ("raw", dict(mean=None, std=None))):
         out = ops.warp_normalize(d, M, (S, S), flip=f, **kw)
         res["%%d_%%s" %% (S, tag)] = hashlib.sha256(out.cpu().numpy().tobytes()).hexdigest()
+    for out in (256, 224, 200):            # LH_INTERP_TORCH: the ring kernel (16-byte aligned rows) vs resize_pairs_kernel
+        r = ops.warp_normalize(d, None, (out, out), interp=ops.LH_INTERP_TORCH)
+        res["%%d_resize_%%d" %% (S, out)] = hashlib.sha256(r.cpu().numpy().tobytes()).hexdigest()
     want = np.stack([R.warp_affine_model(imgs[i], Ms[i], S, S, flip=bool(fl[i])) for i in range(n)]).astype(np.float32)
     raw = ops.warp_normalize(d, M, (S, S), flip=f, mean=None, std=None, layout=ops.LH_LAYOUT_HWC).cpu().numpy()
     res["%%d_model" %% S] = bool(np.array_equal(raw, want))

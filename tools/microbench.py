@@ -76,6 +76,10 @@ def main():
     lut = ops.build_norm_lut(device=dev)
     rec("warp rot+scale lut", timeit(lambda i: ops.warp_normalize(imgs[i], M, (S, S), out=out_img, lut=lut), R), k1_bytes)
     rec("resize torch-mode", timeit(lambda i: ops.warp_normalize(imgs[i], None, (S, S), out=out_img, interp=ops.LH_INTERP_TORCH), R), k1_bytes)
+    imgs224 = [torch.randint(0, 256, (N, 224, 224, 3), device=dev, dtype=torch.uint8, generator=g) for _ in range(R)]
+    rec("resize torch-mode 224->256 (LightHand99K path)",
+        timeit(lambda i: ops.warp_normalize(imgs224[i], None, (S, S), out=out_img, interp=ops.LH_INTERP_TORCH), R),
+        N * (224 * 224 * 3 + S * S * 12))
     # FreiHAND image path (a-3): 224x224 sources, train-time augmentation mix (40 % rotated), 224 -> 256
     import numpy as np
     from lighthand_b200.datasets import frei_dataloader as F
