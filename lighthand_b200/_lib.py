@@ -101,6 +101,7 @@ PROTOTYPES = {
     "lh_pck_curve_accum": (c_i, [c_p, c_p, c_i, c_p, c_p, c_i, c_i64, c_i, c_p, c_i, c_i, c_i,
                                  c_p, c_p, c_p, c_p, c_p]),
     "lh_frei_rgb_processing": (c_i, [c_p, c_i64, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_i, c_p, c_i, c_i, c_p, c_p]),
+    "lh_frei_fused": (c_i, [c_p, c_i64, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_i, c_p, c_i, c_i, c_p, c_i, c_p, c_i, c_i, c_p]),
     "lh_resize_normalize_f32": (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, c_p, c_i, c_i, c_p]),
     "lh_color_jitter_normalize": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "lh_pipeline_create": (c_i, [C.POINTER(PipelineCfg), c_p, c_i, C.POINTER(c_p)]),

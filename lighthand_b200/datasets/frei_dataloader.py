@@ -61,8 +61,13 @@ def frei_batch(images_u8: torch.Tensor, joints_2d, centers, scales, augm=None, w
     pns = [a[1] for a in augm]
     rots = [a[2] for a in augm]
     sc_scales = [a[3] * float(scales[i]) for i, a in enumerate(augm)]
-    img = rgb_processing(images_u8, centers, sc_scales, rots, pns)
-    img = ops.resize_normalize_f32(img, (OUT_SIZE, OUT_SIZE), chan_order=ops.LH_CHAN_BGR)
+    # rgb_processing -> Resize((256, 256)) -> Normalize -> [(2, 1, 0)] in one pass (lh_frei_fused: the 224 x 224 float image
+    # stays in shared memory); bit-identical to rgb_processing(...) followed by ops.resize_normalize_f32(...)
+    recs, scratch_floats, max_wh = image_ops.crop_descriptors(centers, sc_scales, [IMG_RES, IMG_RES], rots, pns)
+    desc = image_ops.descriptors_to_device(recs, images_u8.device)
+    rot_idx = torch.tensor([i for i, r in enumerate(recs) if r.rotated], dtype=torch.int32).to(images_u8.device)
+    img = ops.frei_fused(images_u8, desc, IMG_RES, scratch_floats, max_wh, (OUT_SIZE, OUT_SIZE), chan_order=ops.LH_CHAN_BGR,
+                         rot_index=rot_idx)
     j2d = np.stack([j2d_processing(np.asarray(joints_2d[i]).copy(), centers[i], sc_scales[i], rots[i], augm[i][0])
                     for i in range(n)]) if n else np.zeros((0, 21, 3), np.float32)
     joint_2d = (torch.from_numpy(j2d).float()[:, :, :-1] * 100 + 112) * (OUT_SIZE / IMG_RES)      # :335

@@ -198,6 +198,38 @@ def frei_rgb_processing(images_u8: torch.Tensor, desc: torch.Tensor, res: int, s
     return out
 
 
+def frei_fused(images_u8: torch.Tensor, desc: torch.Tensor, res: int, scratch_floats: int, max_rot_wh: Sequence[int],
+               out_hw: Sequence[int], mean=IMAGENET_MEAN, std=IMAGENET_STD, chan_order: int = LH_CHAN_RGB,
+               rot_index: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """rgb_processing + Resize(out_hw) + Normalize (+ channel order) in one pass (``lh_frei_fused``): the res x res float image
+    never goes to HBM.  Bit-identical to ``frei_rgb_processing`` followed by ``resize_normalize_f32``; falls back to those two
+    when the scale res / out is too large for the fused kernel's shared-memory tile."""
+    require_cuda()
+    lib = _lib.load()
+    images_u8 = _dev(images_u8, torch.uint8, "images")
+    n, sh, sw, _ = images_u8.shape
+    oh, ow = int(out_hw[0]), int(out_hw[1])
+    if 32.0 * res / ow + 2.0 > 32 or 32.0 * res / oh + 2.0 > 32:
+        img = frei_rgb_processing(images_u8, desc, res, scratch_floats, max_rot_wh, rot_index=rot_index)
+        return resize_normalize_f32(img, out_hw, mean, std, chan_order, out)
+    desc = _dev(desc, torch.uint8, "desc")
+    if desc.numel() != n * C.sizeof(_lib.FreiDesc):
+        raise LighthandError("desc: expected N packed lh_frei_desc records")
+    if out is None:
+        out = torch.empty((n, 3, oh, ow), dtype=torch.float32, device=images_u8.device)
+    if n == 0:
+        return out
+    max_w, max_h = int(max_rot_wh[0]), int(max_rot_wh[1])
+    scratch = torch.empty(int(scratch_floats), dtype=torch.float32, device=images_u8.device) if max_w > 0 else None
+    if rot_index is not None:
+        rot_index = _dev(rot_index, torch.int32, "rot_index")
+    with torch.cuda.device(images_u8.device):
+        check(lib.lh_frei_fused(images_u8.data_ptr(), sh * sw * 3, sh, sw, sw * 3, desc.data_ptr(), n, int(res),
+                                _ptr(rot_index), 0 if rot_index is None else rot_index.numel(), _ptr(scratch), max_w, max_h,
+                                _mean_std(mean, std), chan_order, out.data_ptr(), oh, ow, _stream()), "lh_frei_fused")
+    return out
+
+
 def resize_normalize_f32(src: torch.Tensor, out_hw: Sequence[int], mean=IMAGENET_MEAN, std=IMAGENET_STD,
                          chan_order: int = LH_CHAN_RGB, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """transforms.Resize(out_hw) on a float CHW batch + Normalize (+ channel reversal): src [N,3,h,w] float32 CUDA

@@ -127,3 +127,31 @@ def test_empty_batch_and_unrotated_only_batch():
     for i in range(4):
         want = R.frei_rgb_processing(imgs[i], centers[i], float(scales[i]), 0.0, pns[i])
         np.testing.assert_allclose(got[i], want, rtol=0, atol=2e-6)
+
+
+def test_fused_rgb_resize_equals_the_two_kernel_path_bitwise():
+    """lh_frei_fused (rgb_processing's 224 x 224 image kept in shared memory) == lh_frei_rgb_processing followed by
+    lh_resize_normalize_f32, bit for bit: rotated and un-rotated samples, windows sticking out of the image, both channel orders."""
+    import torch
+    from lighthand_b200 import ops
+    from lighthand_b200.datasets import frei_dataloader as F
+    from lighthand_b200.utils import image_ops
+    rng = np.random.RandomState(11)
+    n = 24
+    imgs = torch.from_numpy(np.random.default_rng(3).integers(0, 256, (n, 224, 224, 3), dtype=np.uint8)).cuda()
+    augm = [F.augm_params(True, rng) for _ in range(n)]
+    centers = 112 + rng.uniform(-40, 40, (n, 2))
+    scales = [a[3] * rng.uniform(0.7, 1.3) for a in augm]
+    recs, sfl, mwh = image_ops.crop_descriptors(centers, scales, [224, 224], [a[2] for a in augm], [a[1] for a in augm])
+    assert any(r.rotated for r in recs) and not all(r.rotated for r in recs)
+    desc = image_ops.descriptors_to_device(recs, imgs.device)
+    rot = torch.tensor([i for i, r in enumerate(recs) if r.rotated], dtype=torch.int32).cuda()
+    for order in (ops.LH_CHAN_BGR, ops.LH_CHAN_RGB):
+        two = ops.resize_normalize_f32(ops.frei_rgb_processing(imgs, desc, 224, sfl, mwh, rot_index=rot), (256, 256), chan_order=order)
+        one = ops.frei_fused(imgs, desc, 224, sfl, mwh, (256, 256), chan_order=order, rot_index=rot)
+        assert torch.equal(one, two)
+    # a ragged output size and the fallback for scales the fused tile cannot hold
+    two = ops.resize_normalize_f32(ops.frei_rgb_processing(imgs, desc, 224, sfl, mwh, rot_index=rot), (250, 270))
+    assert torch.equal(ops.frei_fused(imgs, desc, 224, sfl, mwh, (250, 270), rot_index=rot), two)
+    two = ops.resize_normalize_f32(ops.frei_rgb_processing(imgs, desc, 224, sfl, mwh, rot_index=rot), (224, 224))
+    assert torch.equal(ops.frei_fused(imgs, desc, 224, sfl, mwh, (224, 224), rot_index=rot), two)

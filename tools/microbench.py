@@ -102,6 +102,9 @@ def main():
     rec("frei rgb_processing (rotate+resize)", timeit(frei_rgb, R), frei_bytes)
     rec("frei Resize+Normalize+BGR f32", timeit(lambda i: ops.resize_normalize_f32(rgb, (S, S), chan_order=ops.LH_CHAN_BGR, out=out_img), R),
         N * (224 * 224 * 12 + S * S * 12))
+    rec("frei fused rgb_processing+Resize+Normalize+BGR (lh_frei_fused)",
+        timeit(lambda i: ops.frei_fused(fimgs[i], desc, 224, sfl, mpx, (S, S), chan_order=ops.LH_CHAN_BGR, rot_index=rot, out=out_img), R),
+        N * (224 * 224 * 3 + S * S * 12))
     big_src = torch.empty((N, 3, S, S), device=dev)
     rec("torch_copy_201MB", timeit(lambda i: out_img.copy_(big_src), 1), 2 * N * 3 * S * S * 4)
     print(json.dumps(res, indent=1))
