@@ -29,6 +29,9 @@
 #ifndef LH_TMA_MINB
 #define LH_TMA_MINB 6
 #endif
+#ifndef LH_RS_I2F
+#define LH_RS_I2F 1     // resize ring: byte -> float conversions through I2F.U8 (XU pipe): 0 none, 1 half, 2 all -- measured 52.6 / 51.5 / 53.6 us
+#endif
 #ifndef LH_TMA_CTAS
 #define LH_TMA_CTAS 4     // resident CTAs per SM the persistent grid is sized for (measured optimum)
 #endif
@@ -270,12 +273,14 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tm_small, const __grid_const
 // (src/tools/dataset.py:147-157, the LightHand99K dataset path).  Producer: torch's source index / lambda per output column
 // and row of the tile (float32, ATen's fused scale * (dst + 0.5) - 0.5), the tile's source window, one TMA load.  Consumers
 // (lane = output column, 8 rows per warp) interpolate each needed SOURCE row horizontally ONCE -- H(y) = lx0 p(y,x0) +
-// lx1 p(y,x1) per channel, from the raw bytes: 3 LDS + 2 funnel shifts + 7 PRMT + 6 FADD -- and roll (H(y0), H(y1)) down the
-// output rows: up-sampling 224 -> 256 needs 1.14 horizontal passes per output pixel instead of 2, i.e. 6.9 byte->float
+// lx1 p(y,x1) per channel, from the raw bytes: 3 LDS + 2 funnel shifts + 7 PRMT + 6 FADD -- into a per-warp slice of shared
+// memory, then blend (H(y0), H(y1)) per output row: up-sampling 224 -> 256 needs 1.14 horizontal passes per output pixel instead of 2, i.e. 6.9 byte->float
 // conversions instead of 12 (the record-staging kernel resize_pairs_kernel is bound by exactly those).  Same float operations as
 // resize_pairs_kernel (value in byte units, one FMA normalises): identical results.  Right / bottom edge: torch clamps the
 // second tap to the last pixel; here the lane's PRMT selector repeats the first tap's bytes / the row table repeats the row.
 // ------------------------------------------------------------------------------------------------
+constexpr int kHRows = 14;     // source rows 8 output rows can touch: 8 * 1.43 + 2
+
 template <int GEO>
 __global__ void __launch_bounds__(kTmaThreads, LH_TMA_MINB)
 resize_tma_kernel(const __grid_constant__ CUtensorMap tm_small, const __grid_constant__ CUtensorMap tm_large,
@@ -283,6 +288,7 @@ resize_tma_kernel(const __grid_constant__ CUtensorMap tm_small, const __grid_con
     extern __shared__ uint8_t s_dyn[];
     uint8_t* s_base = s_dyn + ((128u - (smem_u32(s_dyn) & 127u)) & 127u);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_base + kStages * kStageBytes2);
+    float* s_h = reinterpret_cast<float*>(s_base + kStages * kStageBytes2 + 64);   // [kConsWarps][kHRows][3][32] horizontal rows
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
 #pragma unroll
@@ -375,8 +381,11 @@ resize_tma_kernel(const __grid_constant__ CUtensorMap tm_small, const __grid_con
                     }
                     if (p.chan_order == LH_CHAN_BGR) { const unsigned tt = i0; i0 = i2; i2 = tt; }
                 }
-                // horizontally interpolated source row y (byte units), all three channels
-                auto hrow = [&](int y, float& hr, float& hg, float& hb) {
+                // pass 1: every source row the warp's 8 output rows touch, horizontally interpolated ONCE (byte units, three
+                // channels) into the warp's slice of shared memory -- no row-to-row dependence, no data-dependent branches
+                const int ys = tab[64 + r0], ye = tab[96 + r0 + rows - 1];           // warp-uniform: first .. last source row
+                float* hbuf = s_h + warp * (kHRows * 3 * 32) + lane;
+                for (int y = ys; y <= ye; ++y) {
                     const uint32_t o = (uint32_t)(y * kBoxW) + org;
                     const uint32_t* q = reinterpret_cast<const uint32_t*>(__cvta_shared_to_generic(o & ~3u));
                     const uint32_t sh = o << 3;
@@ -386,26 +395,31 @@ resize_tma_kernel(const __grid_constant__ CUtensorMap tm_small, const __grid_con
                     auto bytef = [](uint32_t w, uint32_t k) {   // byte k of w as float without I2F: under the exponent of 2^23
                         return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u | k)) - 8388608.0f;
                     };
-                    hr = fmaf(lx1, bytef(t1, 0), lx0 * bytef(lo, 0));
-                    hg = fmaf(lx1, bytef(t1, 1), lx0 * bytef(lo, 1));
-                    hb = fmaf(lx1, bytef(t1, 2), lx0 * bytef(lo, 2));
-                };
-                int cur_lo = -1, cur_hi = -1;
-                float lr = 0.f, lg = 0.f, lb = 0.f, hr = 0.f, hg = 0.f, hb = 0.f;
+                    auto bytei = [](uint32_t w, uint32_t k) { return (float)((w >> (8 * k)) & 0xffu); };   // I2F.U8 (XU pipe)
+                    float* h = hbuf + (y - ys) * (3 * 32);
+#if LH_RS_I2F == 2
+                    h[0] = fmaf(lx1, bytei(t1, 0), lx0 * bytei(lo, 0));
+                    h[32] = fmaf(lx1, bytei(t1, 1), lx0 * bytei(lo, 1));
+                    h[64] = fmaf(lx1, bytei(t1, 2), lx0 * bytei(lo, 2));
+#elif LH_RS_I2F == 1
+                    h[0] = fmaf(lx1, bytef(t1, 0), lx0 * bytef(lo, 0));
+                    h[32] = fmaf(lx1, bytei(t1, 1), lx0 * bytef(lo, 1));
+                    h[64] = fmaf(lx1, bytei(t1, 2), lx0 * bytei(lo, 2));
+#else
+                    h[0] = fmaf(lx1, bytef(t1, 0), lx0 * bytef(lo, 0));
+                    h[32] = fmaf(lx1, bytef(t1, 1), lx0 * bytef(lo, 1));
+                    h[64] = fmaf(lx1, bytef(t1, 2), lx0 * bytef(lo, 2));
+#endif
+                }
+                // pass 2: the 8 output rows, independent of one another (a lane reads back only what it wrote: no barrier)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     if (!GEO && j >= rows) break;
-                    const int y0 = tab[64 + r0 + j], y1 = tab[96 + r0 + j];        // warp-uniform
+                    const float* h0 = hbuf + (tab[64 + r0 + j] - ys) * (3 * 32);
+                    const float* h1 = hbuf + (tab[96 + r0 + j] - ys) * (3 * 32);
                     const float ly1 = __int_as_float(tab[128 + r0 + j]), ly0 = __fsub_rn(1.0f, ly1);
-                    if (y0 != cur_lo) {
-                        if (y0 == cur_hi) { lr = hr; lg = hg; lb = hb; } else hrow(y0, lr, lg, lb);
-                        cur_lo = y0;
-                    }
-                    if (y1 != cur_hi) {
-                        if (y1 == cur_lo) { hr = lr; hg = lg; hb = lb; } else hrow(y1, hr, hg, hb);
-                        cur_hi = y1;
-                    }
-                    const float vr = fmaf(ly1, hr, ly0 * lr), vg = fmaf(ly1, hg, ly0 * lg), vb = fmaf(ly1, hb, ly0 * lb);
+                    const float vr = fmaf(ly1, h1[0], ly0 * h0[0]), vg = fmaf(ly1, h1[32], ly0 * h0[32]),
+                                vb = fmaf(ly1, h1[64], ly0 * h0[64]);
                     const float o0 = fmaf(vr, na0, nb0), o1 = fmaf(vg, na1, nb1), o2 = fmaf(vb, na2, nb2);
                     if (GEO) {
                         __stcs(d0 + j * GEO, o0); __stcs(d0 + GEO * GEO + j * GEO, o1); __stcs(d0 + 2 * GEO * GEO + j * GEO, o2);
@@ -513,7 +527,7 @@ static int launch_geo(const CUtensorMap& ms, const CUtensorMap& ml, const WarpPa
 template <int GEO>
 static int launch_resize_geo(const CUtensorMap& ms, const CUtensorMap& ml, const WarpParams& p, cudaStream_t st) {
     static int cap = 0, sms_cached = 0;
-    const size_t smem = 128 + (size_t)kStages * kStageBytes2 + 64;
+    const size_t smem = 128 + (size_t)kStages * kStageBytes2 + 64 + (size_t)kConsWarps * kHRows * 3 * 32 * sizeof(float);
     if (cap <= 0) {
         int dev = 0, sms = 0, occ = 0;
         if (cudaGetDevice(&dev) != cudaSuccess) return (int)cudaGetLastError();
