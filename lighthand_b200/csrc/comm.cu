@@ -10,6 +10,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstring>
 #include <mutex>
 
 #include "lh_common.cuh"
