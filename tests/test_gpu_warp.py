@@ -179,3 +179,31 @@ print(json.dumps(res))
         outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
     assert outs[0] == outs[1]
     assert all(v is True for k, v in outs[0].items() if k.endswith("_model"))
+
+
+def test_random_affine_matrices_vs_cv2_model(ops):
+    """Arbitrary 2x3 matrices through the TMA-staged kernel (and its non-staged fallback inside the same launch): shear,
+    anisotropic scale from 0.3x to 3x, reflections, translations that push the crop partly or wholly off the source, a
+    singular matrix (cv2 inverts it with D = 0) -- every pixel equal to the cv2 fixed-point model."""
+    rng = np.random.default_rng(77)
+    S = 128
+    n = 24
+    imgs = rng.integers(0, 256, (n, S, S, 3), dtype=np.uint8)
+    Ms = []
+    for i in range(n):
+        ang, shear = rng.uniform(-np.pi, np.pi), rng.uniform(-0.5, 0.5)
+        sx, sy = np.exp(rng.uniform(np.log(0.3), np.log(3.0), 2))
+        A = np.array([[np.cos(ang), -np.sin(ang)], [np.sin(ang), np.cos(ang)]]) @ np.array([[1, shear], [0, 1]]) @ np.diag([sx, sy])
+        if i % 7 == 0:
+            A[:, 0] *= -1                                        # reflection
+        t = rng.uniform(-S, S, 2) if i % 3 else rng.uniform(0, S / 4, 2)
+        Ms.append(np.concatenate([A, t[:, None]], 1).astype(np.float32).astype(np.float64))
+    Ms[5] = np.array([[1.0, 2.0, 3.0], [2.0, 4.0, 5.0]])          # singular
+    Ms[6] = np.array([[1.0, 0.0, 5000.0], [0.0, 1.0, -5000.0]])   # nothing of the source left
+    M = np.stack(Ms)
+    for flip in (False, True):
+        fl = np.full(n, flip, np.uint8)
+        got = ops.warp_normalize(cu(imgs), cu(M), (S, S), flip=cu(fl), mean=None, std=None, layout=ops.LH_LAYOUT_HWC).cpu().numpy()
+        for i in range(n):
+            want = R.warp_affine_model(imgs[i], M[i], S, S, flip=flip).astype(np.float32)
+            assert np.array_equal(got[i], want), (i, flip)
