@@ -457,8 +457,25 @@ def run_ours(args):
         ser_ms.append(_max_over_ranks(t0e.elapsed_time(t1e), dev, world, dist))
         k1s.append(float(np.mean([e[0].elapsed_time(e[1]) for e in ev])))
         fus.append(float(np.mean([ev[i][1].elapsed_time(ev[i + 1][0] if i + 1 < K else ev_last) for i in range(K)])))
-    clocks = sampler.stop() if rank == 0 else None
     metrics = pipe.meter.result()                          # all-reduced totals of the last serial repetition
+    # ---- region C: each kernel ALONE, K back-to-back launches over the ring (what a launch costs when it does not inherit the
+    # other kernel's dirty L2 lines: the write-back of K1's 201 MB output is paid by whatever runs after it) ----------
+    alone = {}
+    st_raw = torch.cuda.current_stream().cuda_stream
+    for name in ("warp_normalize", "heatmap_fused"):
+        reps_c = []
+        for rep in range(max(3, reps_b // 2)):
+            torch.cuda.synchronize()
+            t0e.record()
+            for i in range(K):
+                stp = sets[i % ring]
+                rc = stp._f1(*stp._k1, st_raw) if name == "warp_normalize" else stp._f2(stp._aref, st_raw)
+                assert rc == 0
+            t1e.record()
+            torch.cuda.synchronize()
+            reps_c.append(t0e.elapsed_time(t1e) / K)
+        alone[name] = float(np.median(reps_c))
+    clocks = sampler.stop() if rank == 0 else None
     ms = float(np.median(ov_ms))
     ms_serial = float(np.median(ser_ms))
     per_rank_ms = _gather_ranks(float(np.median(ov_ms)), dev, world, dist)
@@ -558,7 +575,11 @@ def run_ours(args):
                      "timed": "serial region B (CUDA events between the two launches on the launching stream)"},
         "kernels": {"warp_normalize": {"ms": k1_ms, "GBps": k1_bytes / (k1_ms * 1e-3) / 1e9, "bytes": k1_bytes},
                     "heatmap_fused": {"ms": fused_ms, "GBps": fused_bytes / (fused_ms * 1e-3) / 1e9, "bytes": fused_bytes},
-                    "rest_ms": ms_serial / K - k1_ms - fused_ms},
+                    "rest_ms": ms_serial / K - k1_ms - fused_ms,
+                    "alone": {"warp_normalize_ms": alone["warp_normalize"], "heatmap_fused_ms": alone["heatmap_fused"],
+                              "warp_normalize_frac": k1_bytes / (alone["warp_normalize"] * 1e-3) / 1e9 / peak,
+                              "heatmap_fused_frac": fused_bytes / (alone["heatmap_fused"] * 1e-3) / 1e9 / peak,
+                              "note": "K back-to-back launches of ONE kernel over the ring: without the other kernel's dirty L2 lines to write back"}},
         "pipeline_roofline": {"moved_bytes_per_image": ab["step"], "moved_GBps": ab["step"] * B / (step_ms * 1e-3) / 1e9,
                               "moved_frac_of_peak": ab["step"] * B / (step_ms * 1e-3) / 1e9 / peak,
                               "survey_unfused_bytes_per_image": survey_bytes,
