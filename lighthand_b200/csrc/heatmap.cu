@@ -5,18 +5,17 @@
 //   get_max_preds (src/utils/loss.py:327-355) [+ quarter-pixel shift, inverse affine]
 //   PCK_2d_loss / EPE_train (src/utils/loss.py:50-67,116-148) on the decoded joints (optional, fused tail)
 //
-// One CTA of 256 threads owns one (n,j) map.  Threads are laid out 2-D over the map (a thread keeps
-// one 4-float column group and walks down the rows), so the Gaussian-window test in x and the table
-// column offsets are loop invariants; H*W floats are streamed with 16-byte loads/stores, 4 independent
-// vectors in flight per thread.  The target value is recomputed from the joint (a <=31x31 table in
-// shared memory) instead of being re-read.  The argmax keeps the exact numpy order (first index on
-// ties, NaN is the maximum) but tests one NaN-propagating max of the 4 lanes of a vector against the
-// running best and only then falls into the exact per-element update, so the common case costs four
-// instructions per vector.  Loss partials and the argmax are reduced with warp shuffles / REDUX and
-// once across the 8 warps through shared memory.  The last CTA to finish (ticket) adds the per-map
-// partials in index order (deterministic loss) and, if asked, folds the PCK / EPE counts of the batch
-// into the running metric accumulators -- so a whole step's post-backbone work is ONE launch.
-// HBM-bound by construction: it moves H*W*4 B in (+ H*W*4 B per requested output).
+// One WARP owns one (n,j) map (heatmap_warp_kernel below): it streams the map as warp-rows of 32 float4 (512
+// contiguous bytes per load instruction), two register buffers of 4 vectors per lane, and never meets a block
+// barrier.  The target value is recomputed from the joint (a <=31x31 table in shared memory) instead of being
+// re-read.  The argmax keeps the exact numpy order (first index on ties, NaN is the maximum): one NaN-propagating
+// max of the 4 elements of a vector against the lane's running best, REDUX on the order key across the warp, and
+// only the lanes that hold the maximum look at single elements.  Loss partials and the argmax are reduced with
+// shuffles / REDUX inside the warp; the same warp finishes its map (coordinates, PCK / EPE record).  Every CTA
+// leaves one slot of sums; the last CTA to finish (ticket) adds the slots in index order (deterministic loss) and,
+// if asked, folds the PCK / EPE counts of the batch into the running metric accumulators -- so a whole step's
+// post-backbone work is ONE launch.  HBM-bound by construction: it moves H*W*4 B in (+ H*W*4 B per requested
+// output).  Shapes the vector kernel does not take (W % 4 != 0, unaligned pointers) go to heatmap_scalar_kernel.
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -283,8 +282,8 @@ __device__ __noinline__ void finish_map(const HeatmapParams& p, long long m, int
 //
 // Work list (static, interleaved over the CTAs): with Wt resident warps, the first floor(n_maps / Wt) * Wt maps are
 // whole-map units; the REMAINING maps are cut into P = floor(Wt / remaining) pieces of consecutive warp-rows so that
-// the last round keeps every warp busy for 1/P of a map instead of leaving most of them idle (batch 256 x 21 joints
-// on 4736 warps: 4736 whole maps + 640 maps in 7 pieces).  Pieces of one map meet through the workspace: a 64-bit
+// the last round keeps every warp busy for 1/P of a map instead of leaving most of them idle (batch 32 x 21 joints
+// on 3552 warps: 672 maps in 5 pieces each; batch 256: 3552 + 1824 whole maps, P = 1).  Pieces of one map meet through the workspace: a 64-bit
 // atomicMax on (order key << 32 | ~index) -- maximum value first, then the smallest index = numpy's tie-break -- and a
 // counter; the piece that arrives last finishes the map and leaves both words zeroed.  Loss partials never meet per
 // map: every unit adds to its warp's float64 sum, warps are combined per CTA in warp order, CTAs by the last CTA in
