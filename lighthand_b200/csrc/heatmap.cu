@@ -118,6 +118,13 @@ __device__ __forceinline__ float target_at(const Window& w, const float* s_tab, 
     return 0.0f;
 }
 
+// ticket = atomicAdd(ticket, 1) with acquire-release semantics at GPU scope
+__device__ __forceinline__ unsigned int ticket_acq_rel(unsigned int* ticket) {
+    unsigned int old;
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(ticket) : "memory");
+    return old;
+}
+
 __device__ __forceinline__ float max_nan(float a, float b) {
     float r;
     asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
@@ -139,41 +146,42 @@ __device__ __forceinline__ float bbox_diag_seq(const float* g, int J, int gs) {
     return __fsqrt_rn(__fadd_rn(__fmul_rn(w, w), __fmul_rn(h, h)));
 }
 
+// bbox diagonal of sample n across the warp (PCK "proportion" mode): the reference's builtin max() / min() keep the
+// first element unless a later one compares strictly greater / smaller, so a NaN survives only as the first joint
+// -> NaN-ignoring reduce, then patch.  `jl` = this lane's ground-truth joint (lane < J <= 32), else read from memory.
+__device__ __forceinline__ float bbox_diag_warp(const HeatmapParams& p, long long n, float2 jl, float2 jfirst, int lane) {
+    const float nan = __int_as_float(0x7fc00000);
+    float mxx = nan, mnx = nan, mxy = nan, mny = nan;
+    if (p.J <= 32) {
+        if (lane < p.J) { mxx = mnx = jl.x; mxy = mny = jl.y; }
+    } else {
+        const float* g = p.joints + n * p.J * p.joint_stride;
+        for (int j = lane; j < p.J; j += 32) {
+            const float x = g[j * p.joint_stride], y = g[j * p.joint_stride + 1];
+            mxx = fmaxf(mxx, x); mnx = fminf(mnx, x); mxy = fmaxf(mxy, y); mny = fminf(mny, y);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+        mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+        mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+    }
+    if (jfirst.x != jfirst.x) { mxx = jfirst.x; mnx = jfirst.x; }
+    if (jfirst.y != jfirst.y) { mxy = jfirst.y; mny = jfirst.y; }
+    const float w = __fsub_rn(mxx, mnx), h = __fsub_rn(mxy, mny);
+    return __fsqrt_rn(__fadd_rn(__fmul_rn(w, w), __fmul_rn(h, h)));
+}
+
 // ------------------------------------------------------------------------------------------------
 // Tail of one map: final argmax -> coordinates (+ sub-pixel / inverse affine), outputs, fused metric
-// record.  Runs on warp 0 (lanes cooperate on the bbox diagonal); `jl` = this lane's ground-truth
-// joint of sample n (lane < J), `gj` = the map's own joint.
+// record.  Lane 0 of the owning warp; m = n * J + j, `diag` = the sample's bbox diagonal (bbox_diag_warp), `gj` =
+// the map's own joint.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void map_tail(const HeatmapParams& p, long long m, const float* pred, int bi, float mv,
-                                         bool do_metric, float2 jl, float2 jfirst, float2 gj, int lane,
+__device__ __forceinline__ void map_tail(const HeatmapParams& p, long long m, long long n, int j, const float* pred, int bi,
+                                         float mv, bool do_metric, float diag, float2 gj, int lane,
                                          double& epe_acc, unsigned int& wrong_acc) {
-    float diag = 0.f;
-    if (do_metric && p.pck_mode == LH_PCK_PROPORTION) {
-        // builtin max()/min() of the reference keep the first element unless a later one compares strictly
-        // greater / smaller: a NaN survives only as the first joint -> NaN-ignoring reduce, then patch.
-        const float nan = __int_as_float(0x7fc00000);
-        float mxx = nan, mnx = nan, mxy = nan, mny = nan;
-        if (p.J <= 32) {
-            if (lane < p.J) { mxx = mnx = jl.x; mxy = mny = jl.y; }
-        } else {
-            const float* g = p.joints + (m / p.J) * p.J * p.joint_stride;
-            for (int j = lane; j < p.J; j += 32) {
-                const float x = g[j * p.joint_stride], y = g[j * p.joint_stride + 1];
-                mxx = fmaxf(mxx, x); mnx = fminf(mnx, x); mxy = fmaxf(mxy, y); mny = fminf(mny, y);
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
-            mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
-            mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
-            mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
-        }
-        if (jfirst.x != jfirst.x) { mxx = jfirst.x; mnx = jfirst.x; }
-        if (jfirst.y != jfirst.y) { mxy = jfirst.y; mny = jfirst.y; }
-        const float w = __fsub_rn(mxx, mnx), h = __fsub_rn(mxy, mny);
-        diag = __fsqrt_rn(__fadd_rn(__fmul_rn(w, w), __fmul_rn(h, h)));
-    }
     if (lane != 0) return;
     const int iy = bi / p.W, ix = bi - iy * p.W;
     float cx = (float)ix, cy = (float)iy;
@@ -191,7 +199,7 @@ __device__ __forceinline__ void map_tail(const HeatmapParams& p, long long m, co
     cx = __fmul_rn(cx, p.out_scale);
     cy = __fmul_rn(cy, p.out_scale);
     if (p.inv_affine) {
-        const double* A = p.inv_affine + (m / p.J) * 6;
+        const double* A = p.inv_affine + n * 6;
         const double x = (double)cx, y = (double)cy;
         const double ox = __dadd_rn(__dadd_rn(__dmul_rn(A[0], x), __dmul_rn(A[1], y)), A[2]);
         const double oy = __dadd_rn(__dadd_rn(__dmul_rn(A[3], x), __dmul_rn(A[4], y)), A[5]);
@@ -208,7 +216,6 @@ __device__ __forceinline__ void map_tail(const HeatmapParams& p, long long m, co
         const float cmp = (p.pck_mode == LH_PCK_PROPORTION) ? __fdiv_rn(d, diag) : d;
         wrong_acc += (cmp > p.pck_thr) ? 1u : 0u;
         // EPE_train keeps joints 1 .. J-2 (range(1, len(distance)) drops the last one too)
-        const int j = (int)(m % p.J);
         if (j >= 1 && j <= p.J - 2) epe_acc += (double)d;
     }
 }
@@ -243,8 +250,8 @@ __device__ __forceinline__ void final_reduce(const HeatmapParams& p, bool do_met
             if (p.loss_f32) *p.loss_f32 = (float)loss;
             if (p.loss_meter) {  // AverageMeter.update(loss.item(), batch_size): float32 loss, stream-ordered
                 const double nb = (double)(p.n_maps / p.J);
-                p.loss_meter[0] += (double)(float)loss * nb;
-                p.loss_meter[1] += nb;
+                atomicAdd(p.loss_meter + 0, (double)(float)loss * nb);   // single writer per launch, stream-ordered: a
+                atomicAdd(p.loss_meter + 1, nb);                         // RED instead of a dependent load round trip
             }
         }
         if (do_metric) {
@@ -262,10 +269,10 @@ __device__ __forceinline__ void final_reduce(const HeatmapParams& p, bool do_met
 
 // The map's tail as a separate function (its registers -- FP64 inverse affine, bbox reduction -- stay out of the
 // streaming loop's allocation).  Whole warp; the joints were fetched at the head of the unit.
-__device__ __noinline__ void finish_map(const HeatmapParams& p, long long m, int bi, float mv, bool do_metric, float2 jl,
-                                        float2 jfirst, float2 gj, int lane, double& epe_acc, unsigned int& wrong_acc) {
+__device__ __noinline__ void finish_map(const HeatmapParams& p, int m, int jm, int bi, float mv, bool do_metric, float diag,
+                                        float2 gj, int lane, double& epe_acc, unsigned int& wrong_acc) {
     if (bi == 0x7fffffff) bi = 0;    // HW == 0 only
-    map_tail(p, m, p.pred + (size_t)m * p.HW, bi, mv, do_metric, jl, jfirst, gj, lane, epe_acc, wrong_acc);
+    map_tail(p, m, (m - jm) / p.J, jm, p.pred + (size_t)m * p.HW, bi, mv, do_metric, diag, gj, lane, epe_acc, wrong_acc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -363,8 +370,8 @@ __global__ void __launch_bounds__(kWarpThreads, TSRC == 2 ? 3 : LH_HM_MINB) heat
         float2 jl = make_float2(0.f, 0.f), gj = jl, jfirst = jl;
         float vis = 1.0f;                                        // the map's joint visibility (use_vis only)
         const bool need_j = (TSRC == 1) || do_metric;
+        const int jm = m % p.J;
         if (need_j) {
-            const int jm = m % p.J;
             const float* jp = p.joints + (long long)m * p.joint_stride;
             if (TSRC == 1 && p.use_vis) vis = jp[2];
             if (p.J <= 32) {
@@ -380,6 +387,9 @@ __global__ void __launch_bounds__(kWarpThreads, TSRC == 2 ? 3 : LH_HM_MINB) heat
                 jfirst = make_float2(gp[0], gp[1]);
             }
         }
+        // the sample's bbox diagonal (PCK normaliser) now, while the first chunk is in flight -- not in the unit's tail
+        float diag = 0.f;
+        if (do_metric && p.pck_mode == LH_PCK_PROPORTION) diag = bbox_diag_warp(p, (m - jm) / p.J, jl, jfirst, lane);
         int ulx = 0, uly = 0, wwin = 0, hwin = 0;
         float wgt = 1.0f, gs = p.grad_scale;
         if (TSRC == 1) {
@@ -495,7 +505,7 @@ __global__ void __launch_bounds__(kWarpThreads, TSRC == 2 ? 3 : LH_HM_MINB) heat
                 mv = __shfl_sync(0xffffffffu, mv, 0);
                 finish = last != 0;
             }
-            if (finish) finish_map(p, m, bi, mv, do_metric, jl, jfirst, gj, lane, epe_acc, wrong_acc);
+            if (finish && lane == 0) finish_map(p, m, jm, bi, mv, do_metric, diag, gj, lane, epe_acc, wrong_acc);
         }
     }
 
@@ -509,15 +519,14 @@ __global__ void __launch_bounds__(kWarpThreads, TSRC == 2 ? 3 : LH_HM_MINB) heat
 #pragma unroll
             for (int w = 0; w < kWarpsPerCta; ++w) { cl += s_wl[w]; ce += s_we[w]; cw += s_ww[w]; }
             p.cta_loss[blockIdx.x] = cl; p.cta_epe[blockIdx.x] = ce; p.cta_wrong[blockIdx.x] = cw;
-            __threadfence();
-            const unsigned int t = atomicAdd(p.ticket, 1u);
+            // release our slot / acquire everybody else's in ONE acq_rel atomic: __threadfence() is a sequentially
+            // consistent fence (MEMBAR.SC) and the pair fence + atomic + fence sat on the kernel's critical path --
+            // only the LAST CTA's tail is exposed, but it is exposed in full (fused pass)
+            const unsigned int t = ticket_acq_rel(p.ticket);
             s_last = (t == gridDim.x - 1);
         }
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            final_reduce<LOSS, kWarpThreads>(p, do_metric, s_fa, s_fb, s_fc, tid);
-        }
+        __syncthreads();      // orders the other threads' slot loads (ld.cg, L2) after thread 0's acquire
+        if (s_last) final_reduce<LOSS, kWarpThreads>(p, do_metric, s_fa, s_fb, s_fc, tid);
     }
 }
 
@@ -625,7 +634,10 @@ __global__ void __launch_bounds__(kThreads) heatmap_scalar_kernel(const HeatmapP
                 if (s_key[w] > bk || (s_key[w] == bk && s_idx[w] < bi)) { bk = s_key[w]; bi = s_idx[w]; }
             }
             if (bi == 0x7fffffff) bi = 0;
-            map_tail(p, m, pred, bi, pred[bi], do_metric, jl, jfirst, gj, lane, cta_epe, cta_wrong);
+            const long long n = m / p.J;
+            float diag = 0.f;
+            if (do_metric && p.pck_mode == LH_PCK_PROPORTION) diag = bbox_diag_warp(p, n, jl, jfirst, lane);
+            map_tail(p, m, n, (int)(m - n * p.J), pred, bi, pred[bi], do_metric, diag, gj, lane, cta_epe, cta_wrong);
         }
     }
     if ((do_loss && (p.loss_f64 || p.loss_f32 || p.loss_meter)) || do_metric) {
