@@ -37,73 +37,93 @@ __device__ __forceinline__ void image_px(const uint8_t* org, int pitch, int cx, 
     v[0] = (float)__ldg(q); v[1] = (float)__ldg(q + 1); v[2] = (float)__ldg(q + 2);
 }
 
+// byte k of w as a float: PRMT puts it under the exponent of 2^23, one FADD takes the 2^23 off again -- two full-rate
+// instructions instead of a shift / mask and a quarter-rate I2F, and exact
+__device__ __forceinline__ float byte_f(uint32_t w, uint32_t k) {
+    return __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7650u + k)) - 8388608.0f;
+}
+
 // pixels (cx, cy) and (cx + 1, cy), both inside the image, rows 4-byte aligned: the six bytes through three aligned 32-bit
-// loads + two funnel shifts instead of six byte loads
+// loads + two funnel shifts instead of six byte loads.  `row` = the image row, `woff` = (3 * cx) & ~3, `sh` = (3 * cx) << 3.
+__device__ __forceinline__ void row_px2(const uint8_t* row, unsigned woff, unsigned sh, float (&v0)[3], float (&v1)[3]) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(row + woff);
+    const uint32_t a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    const uint32_t lo = __funnelshift_r(a, b, sh), hi = __funnelshift_r(b, c, sh);   // R0 G0 B0 R1 | G1 B1 - -
+    v0[0] = byte_f(lo, 0); v0[1] = byte_f(lo, 1); v0[2] = byte_f(lo, 2);
+    v1[0] = byte_f(lo, 3); v1[1] = byte_f(hi, 0); v1[2] = byte_f(hi, 1);
+}
 __device__ __forceinline__ void image_px2(const uint8_t* org, int pitch, int cx, int cy, float (&v0)[3], float (&v1)[3]) {
     const unsigned off = (unsigned)(3 * cx);
-    const uint32_t* q = reinterpret_cast<const uint32_t*>(org + (long long)cy * pitch + (off & ~3u));
-    const uint32_t a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
-    const uint32_t sh = off << 3;                                 // funnel shifts use (off & 3) * 8
-    const uint32_t lo = __funnelshift_r(a, b, sh), hi = __funnelshift_r(b, c, sh);   // R0 G0 B0 R1 | G1 B1 - -
-    v0[0] = (float)(lo & 0xffu); v0[1] = (float)((lo >> 8) & 0xffu); v0[2] = (float)((lo >> 16) & 0xffu);
-    v1[0] = (float)(lo >> 24); v1[1] = (float)(hi & 0xffu); v1[2] = (float)((hi >> 8) & 0xffu);
+    row_px2(org + (long long)cy * pitch, off & ~3u, off << 3, v0, v1);
 }
 
 constexpr int kFreiTileW = 32, kFreiTileH = kFreiThreads / 32;
 
-// CTA = a 32 x 8 tile of the rotated canvas of one rotated sample (blockIdx.z indexes rot_index): the FP64 row and
-// column terms of cv2's coordinate grid are computed once per tile (40 threads), not once per pixel
+// CTA = a 32 x 32 tile of the rotated canvas of one rotated sample (blockIdx.z indexes rot_index), a thread renders 4 pixels
+// of one column: the FP64 row and column terms of cv2's coordinate grid are computed once per tile (64 threads), not once
+// per pixel, and the taps of the four pixels are in flight together.  (Round 2: 32 x 8 tiles spent their time in that
+// prologue -- descriptor load -> FP64 terms -> barrier -> taps -> store is one latency chain per CTA, 25 k CTAs per batch.)
+constexpr int kRotTileH = 32;
+
 __global__ void __launch_bounds__(kFreiThreads) frei_rotate_kernel(const uint8_t* __restrict__ src, long long img_stride,
                                                                    int sh, int sw, int pitch,
                                                                    const lh_frei_desc* __restrict__ desc,
                                                                    const int32_t* __restrict__ rot_index,
                                                                    float* __restrict__ scratch) {
-    __shared__ int s_ax[kFreiTileW], s_bx[kFreiTileW], s_x0[kFreiTileH], s_y0[kFreiTileH];
+    __shared__ int s_ax[kFreiTileW], s_bx[kFreiTileW], s_x0[kRotTileH], s_y0[kRotTileH];
     const int n = rot_index ? rot_index[blockIdx.z] : blockIdx.z;
     const lh_frei_desc& d = desc[n];
     if (!d.rotated) return;
-    const int pad = d.pad, iw = d.cw - 2 * pad, ih = d.ch - 2 * pad;
-    const int tx0 = blockIdx.x * kFreiTileW, ty0 = blockIdx.y * kFreiTileH;
+    const int pad = d.pad, cw = d.cw, ch = d.ch, iw = cw - 2 * pad, ih = ch - 2 * pad;
+    const int tx0 = blockIdx.x * kFreiTileW, ty0 = blockIdx.y * kRotTileH;
     if (tx0 >= iw || ty0 >= ih) return;                                  // uniform per CTA
     const int tid = threadIdx.x;
     if (tid < kFreiTileW) {
         s_ax[tid] = col_term(d.iM[0], tx0 + tid + pad);                  // position in the padded canvas warpAffine renders
         s_bx[tid] = col_term(d.iM[3], tx0 + tid + pad);
-    } else if (tid < kFreiTileW + kFreiTileH) {
+    } else if (tid < kFreiTileW + kRotTileH) {
         const int r = tid - kFreiTileW;
         s_x0[r] = row_term(d.iM[1], d.iM[2], ty0 + r + pad);
         s_y0[r] = row_term(d.iM[4], d.iM[5], ty0 + r + pad);
     }
     __syncthreads();
-    const int lx = tid & 31, ly = tid >> 5;
-    const int x = tx0 + lx, y = ty0 + ly;
-    if (x >= iw || y >= ih) return;
-    const int X = (s_x0[ly] + s_ax[lx]) >> 5, Y = (s_y0[ly] + s_bx[lx]) >> 5;
-    const int ix = clamp_i(X >> 5, -32768, 32767), iy = clamp_i(Y >> 5, -32768, 32767);   // cv2 stores shorts
-    const float fx = (float)(X & 31) * 0.03125f, fy = (float)(Y & 31) * 0.03125f;
-    const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+    const int lx = tid & 31, wy = tid >> 5;
+    const int x = tx0 + lx;
+    if (x >= iw) return;
+    const int ax = s_ax[lx], bx = s_bx[lx];
+    const int ulx = d.ulx, uly = d.uly;
     const uint8_t* img = src + (long long)n * img_stride;
-    float p00[3], p01[3], p10[3], p11[3];
-    // all four taps inside the canvas and inside the image: no per-tap tests
-    const int gx = d.ulx + ix, gy = d.uly + iy;
     const bool words = ((reinterpret_cast<uintptr_t>(img) | (uintptr_t)pitch) & 3u) == 0;      // uniform
-    if (ix >= 0 && iy >= 0 && ix + 1 < d.cw && iy + 1 < d.ch && gx >= 0 && gy >= 0 && gx + 1 < sw && gy + 1 < sh) {
-        if (words && 3 * gx + 12 <= pitch) {          // the third word stays inside the row
-            image_px2(img, pitch, gx, gy, p00, p01); image_px2(img, pitch, gx, gy + 1, p10, p11);
-        } else {
-            image_px(img, pitch, gx, gy, p00); image_px(img, pitch, gx + 1, gy, p01);
-            image_px(img, pitch, gx, gy + 1, p10); image_px(img, pitch, gx + 1, gy + 1, p11);
-        }
-    } else {
-        canvas_px(img, pitch, sh, sw, d, ix, iy, p00);
-        canvas_px(img, pitch, sh, sw, d, ix + 1, iy, p01);
-        canvas_px(img, pitch, sh, sw, d, ix, iy + 1, p10);
-        canvas_px(img, pitch, sh, sw, d, ix + 1, iy + 1, p11);
-    }
-    float* out = scratch + d.scratch_off + ((size_t)y * iw + x) * 3;
+    float* out = scratch + d.scratch_off + ((size_t)(ty0 + wy) * iw + x) * 3;
+    constexpr int kStep = kFreiThreads / 32;
 #pragma unroll
-    for (int c = 0; c < 3; ++c)    // every product and partial sum is exact in float32 (<= 18 bits)
-        out[c] = p00[c] * w00 + p01[c] * w01 + p10[c] * w10 + p11[c] * w11;
+    for (int k = 0; k < kRotTileH / kStep; ++k, out += (size_t)kStep * iw * 3) {
+        const int ly = wy + k * kStep;
+        if (ty0 + ly >= ih) break;
+        const int X = (s_x0[ly] + ax) >> 5, Y = (s_y0[ly] + bx) >> 5;
+        const int ix = clamp_i(X >> 5, -32768, 32767), iy = clamp_i(Y >> 5, -32768, 32767);   // cv2 stores shorts
+        const float fx = (float)(X & 31) * 0.03125f, fy = (float)(Y & 31) * 0.03125f;
+        const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+        float p00[3], p01[3], p10[3], p11[3];
+        // all four taps inside the canvas and inside the image: no per-tap tests
+        const int gx = ulx + ix, gy = uly + iy;
+        if (ix >= 0 && iy >= 0 && ix + 1 < cw && iy + 1 < ch && gx >= 0 && gy >= 0 && gx + 1 < sw && gy + 1 < sh) {
+            if (words && 3 * gx + 12 <= pitch) {          // the third word stays inside the row
+                image_px2(img, pitch, gx, gy, p00, p01); image_px2(img, pitch, gx, gy + 1, p10, p11);
+            } else {
+                image_px(img, pitch, gx, gy, p00); image_px(img, pitch, gx + 1, gy, p01);
+                image_px(img, pitch, gx, gy + 1, p10); image_px(img, pitch, gx + 1, gy + 1, p11);
+            }
+        } else {
+            canvas_px(img, pitch, sh, sw, d, ix, iy, p00);
+            canvas_px(img, pitch, sh, sw, d, ix + 1, iy, p01);
+            canvas_px(img, pitch, sh, sw, d, ix, iy + 1, p10);
+            canvas_px(img, pitch, sh, sw, d, ix + 1, iy + 1, p11);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)    // every product and partial sum is exact in float32 (<= 18 bits)
+            out[c] = p00[c] * w00 + p01[c] * w01 + p10[c] * w10 + p11[c] * w11;
+    }
 }
 
 // cv2.resize's source index / weight for destination index d (resize.cpp, INTER_LINEAR, CV_64F): double
@@ -240,20 +260,28 @@ __global__ void __launch_bounds__(kFreiThreads) resize_f32_kernel(const float* _
 // 256-image batch less HBM traffic (154 MB written + 154 MB read back) and one launch less.
 // ------------------------------------------------------------------------------------------------
 constexpr int kFuseTile = 32;
+constexpr int kFuseTilesPerCta = 2;      // vertically adjacent tiles per CTA: the column tables and the descriptor are set up once
 
-__global__ void __launch_bounds__(kFreiThreads) frei_fused_kernel(const uint8_t* __restrict__ src, long long img_stride,
+#ifndef LH_FREI_MINB
+#define LH_FREI_MINB 6
+#endif
+__global__ void __launch_bounds__(kFreiThreads, LH_FREI_MINB) frei_fused_kernel(const uint8_t* __restrict__ src, long long img_stride,
                                                                   int sh, int sw, int pitch,
                                                                   const lh_frei_desc* __restrict__ desc,
                                                                   const float* __restrict__ scratch, int res,
                                                                   float* __restrict__ dst, int oh, int ow, float sy, float sx,
                                                                   float na0, float na1, float na2, float nb0, float nb1,
                                                                   float nb2, int chan_order) {
-    __shared__ float s_im[3][kFuseTile][kFuseTile + 1];                       // the rectangle of the intermediate image
-    __shared__ int s_ox0[kFuseTile], s_ox1[kFuseTile], s_oy0[kFuseTile], s_oy1[kFuseTile];     // stage T taps (rectangle-relative)
-    __shared__ float s_olx[kFuseTile], s_oly[kFuseTile];
-    __shared__ int s_x0[kFuseTile], s_x1[kFuseTile], s_y0[kFuseTile], s_y1[kFuseTile];         // stage S taps per rectangle column / row
-    __shared__ float s_a0[kFuseTile], s_a1[kFuseTile], s_b0[kFuseTile], s_b1[kFuseTile];
-    __shared__ int s_reg[4];                                                   // rx_lo, ry_lo, rw, rh
+    constexpr int kRows = kFuseTile * kFuseTilesPerCta;
+#ifndef LH_FREI_BUFS
+#define LH_FREI_BUFS 2
+#endif
+    constexpr int kBufs = LH_FREI_BUFS;                                      // 1: a barrier between tiles; 2: one rectangle buffer per tile (7 CTAs / SM)
+    __shared__ float s_im[kBufs][3][kFuseTile][kFuseTile + 1];               // the rectangle of the intermediate image
+    __shared__ int s_ox0[kFuseTile], s_ox1[kFuseTile], s_oy0[kRows], s_oy1[kRows];             // stage T taps (absolute)
+    __shared__ float s_olx[kFuseTile], s_oly[kRows];
+    __shared__ int s_x0[kFuseTile], s_x1[kFuseTile], s_y0[kRows], s_y1[kRows];                 // stage S taps per rectangle column / row
+    __shared__ float s_a0[kFuseTile], s_a1[kFuseTile], s_b0[kRows], s_b1[kRows];
 
     const int n = blockIdx.z;
     const lh_frei_desc& d = desc[n];
@@ -261,14 +289,14 @@ __global__ void __launch_bounds__(kFreiThreads) frei_fused_kernel(const uint8_t*
     const int pad = rotated ? d.pad : 0;
     const int iw = d.cw - 2 * pad, ih = d.ch - 2 * pad;
     const int tid = threadIdx.x;
-    const int tx0 = blockIdx.x * kFuseTile, ty0 = blockIdx.y * kFuseTile;
-    const int ncol = min(kFuseTile, ow - tx0), nrow = min(kFuseTile, oh - ty0);
+    const int tx0 = blockIdx.x * kFuseTile, ty0 = blockIdx.y * kRows;
+    const int ncol = min(kFuseTile, ow - tx0), nrows = min(kRows, oh - ty0);
 
-    // ---- stage T tables: torch's source index / lambda for the tile's output columns and rows ------------------
-    if (tid < 2 * kFuseTile) {
+    // ---- stage T tables: torch's source index / lambda for the CTA's output columns and rows ----------------------
+    if (tid < kFuseTile + kRows) {
         const bool is_row = tid >= kFuseTile;
         const int t = is_row ? tid - kFuseTile : tid;
-        const int o = (is_row ? ty0 : tx0) + min(t, (is_row ? nrow : ncol) - 1);
+        const int o = (is_row ? ty0 : tx0) + min(t, (is_row ? nrows : ncol) - 1);
         float f = fmaf(is_row ? sy : sx, __fadd_rn((float)o, 0.5f), -0.5f);   // ATen: one fused multiply-add
         f = f < 0.f ? 0.f : f;
         const int i0 = min((int)f, res - 1), i1 = min(i0 + 1, res - 1);
@@ -277,90 +305,131 @@ __global__ void __launch_bounds__(kFreiThreads) frei_fused_kernel(const uint8_t*
         else        { s_ox0[t] = i0; s_ox1[t] = i1; s_olx[t] = l1; }
     }
     __syncthreads();
-    if (tid == 0) {
-        s_reg[0] = s_ox0[0]; s_reg[1] = s_oy0[0];
-        s_reg[2] = s_ox1[ncol - 1] - s_ox0[0] + 1; s_reg[3] = s_oy1[nrow - 1] - s_oy0[0] + 1;
-    }
-    __syncthreads();
-    const int rx_lo = s_reg[0], ry_lo = s_reg[1], rw = s_reg[2], rh = s_reg[3];   // rw, rh <= 32 (launcher checks the scale)
+    // the rectangle of the intermediate image the taps touch: columns once, rows per tile (rw, rh <= 32: the launcher checks the scale)
+    const int rx_lo = s_ox0[0], rw = s_ox1[ncol - 1] - rx_lo + 1;
 
-    // ---- stage S tables for the rectangle's columns / rows ----------------------------------------------------------
+    // ---- stage S tables for the rectangles' columns / rows -----------------------------------------------------------
     if (iw > 0 && ih > 0) {
-        if (tid < rw) cv2_linear_axis(rx_lo + tid, iw, d.scale_x, s_x0[tid], s_x1[tid], s_a0[tid], s_a1[tid]);
-        else if (tid >= kFuseTile && tid < kFuseTile + rh)
-            cv2_linear_axis(ry_lo + tid - kFuseTile, ih, d.scale_y, s_y0[tid - kFuseTile], s_y1[tid - kFuseTile],
-                            s_b0[tid - kFuseTile], s_b1[tid - kFuseTile]);
+        if (tid < rw) {
+            cv2_linear_axis(rx_lo + tid, iw, d.scale_x, s_x0[tid], s_x1[tid], s_a0[tid], s_a1[tid]);
+        } else if (tid >= kFuseTile && tid < kFuseTile + kRows) {
+            const int t = tid - kFuseTile, tile = t / kFuseTile, r = t - tile * kFuseTile;
+            const int row0 = tile * kFuseTile, nr = min(kFuseTile, nrows - row0);
+            if (nr > 0) {
+                const int ry_lo = s_oy0[row0], rh = s_oy1[row0 + nr - 1] - ry_lo + 1;
+                if (r < rh) cv2_linear_axis(ry_lo + r, ih, d.scale_y, s_y0[t], s_y1[t], s_b0[t], s_b1[t]);
+            }
+        }
     }
     __syncthreads();
 
-    // ---- stage S: the rectangle of rgb_processing's image into shared memory --------------------------------------
     const uint8_t* img = src + (long long)n * img_stride;
     const bool words = ((reinterpret_cast<uintptr_t>(img) | (uintptr_t)pitch) & 3u) == 0;      // uniform
     const float pn[3] = {d.pn[0], d.pn[1], d.pn[2]};
-    for (int idx = tid; idx < rw * rh; idx += kFreiThreads) {
-        const int ly = idx / rw, lx = idx - ly * rw;
-        float v3[3] = {0.f, 0.f, 0.f};
-        if (iw > 0 && ih > 0) {
-            const int x0 = s_x0[lx], x1 = s_x1[lx], y0 = s_y0[ly], y1 = s_y1[ly];
-            const float a0 = s_a0[lx], a1 = s_a1[lx], b0 = s_b0[ly], b1 = s_b1[ly];
-            float p00[3], p01[3], p10[3], p11[3];
-            if (rotated) {
-                const float* r0 = scratch + d.scratch_off + (size_t)y0 * iw * 3;
-                const float* r1 = scratch + d.scratch_off + (size_t)y1 * iw * 3;
+    const float na[3] = {na0, na1, na2}, nb[3] = {nb0, nb1, nb2};
+    const int ulx = d.ulx, uly = d.uly;
+    const int lx = tid & 31, wy = tid >> 5;
+    constexpr int kRowStep = kFreiThreads / 32, kPasses = kFuseTile / kRowStep;
+    constexpr int kPitchS = kFuseTile + 1, kPlane = kFuseTile * kPitchS;       // floats per rectangle row / channel plane
+    // this lane's rectangle column (stage S) and output column (stage T): the same for every tile of the CTA
+    const bool s_col = lx < rw && iw > 0 && ih > 0;
+    const int x0 = s_col ? s_x0[lx] : 0, x1 = s_col ? s_x1[lx] : 0;
+    const float a0 = s_col ? s_a0[lx] : 0.f, a1 = s_col ? s_a1[lx] : 0.f;
+    const int gx0 = ulx + x0, gx1 = ulx + x1;
+    const bool col_in = gx0 >= 0 && gx1 < sw;
+    const bool pair_ok = words && col_in && gx1 == gx0 + 1 && 3 * gx0 + 12 <= pitch;
+    const unsigned boff = (unsigned)(3 * gx0), woff = boff & ~3u, bsh = boff << 3;
+    const float* rot0 = rotated ? scratch + d.scratch_off + 3 * x0 : nullptr;  // rotated canvas: this column's two taps
+    const float* rot1 = rotated ? scratch + d.scratch_off + 3 * x1 : nullptr;
+    const bool t_col = lx < ncol;
+    const int ox0 = t_col ? s_ox0[lx] - rx_lo : 0, ox1 = t_col ? s_ox1[lx] - rx_lo : 0;
+    const float lx1 = t_col ? s_olx[lx] : 0.f, lx0 = __fsub_rn(1.0f, lx1);
+    const size_t plane = (size_t)oh * ow;
+    const int c0 = (chan_order == LH_CHAN_BGR) ? 2 : 0, c2 = 2 - c0;           // output plane of channels 0 and 2
+    float* const obase = dst + (size_t)n * 3 * plane + (size_t)(ty0 + wy) * ow + tx0 + lx;
+
+#pragma unroll 1
+    for (int tile = 0; tile < kFuseTilesPerCta; ++tile) {
+        const int row0 = tile * kFuseTile, nrow = min(kFuseTile, nrows - row0);
+        if (nrow <= 0) break;                                                                   // uniform
+        const int ry_lo = s_oy0[row0], rh = s_oy1[row0 + nrow - 1] - ry_lo + 1;
+        float* const im = &s_im[tile % kBufs][0][0][0];
+
+        // ---- stage S: the rectangle of rgb_processing's image into shared memory (lane = column, 8 rows per pass) ---
+        if (lx < rw) {
+            float* sp = im + wy * kPitchS + lx;
+#pragma unroll
+            for (int k = 0; k < kPasses; ++k, sp += kRowStep * kPitchS) {
+                const int ly = wy + k * kRowStep;
+                if (ly >= rh) break;
+                float v3[3] = {0.f, 0.f, 0.f};
+                if (s_col) {
+                    const int y0 = s_y0[row0 + ly], y1 = s_y1[row0 + ly];
+                    const float b0 = s_b0[row0 + ly], b1 = s_b1[row0 + ly];
+                    float p00[3], p01[3], p10[3], p11[3];
+                    if (rotated) {
+                        const size_t r0 = (size_t)y0 * iw * 3, r1 = (size_t)y1 * iw * 3;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            p00[c] = __ldg(rot0 + r0 + c); p01[c] = __ldg(rot1 + r0 + c);
+                            p10[c] = __ldg(rot0 + r1 + c); p11[c] = __ldg(rot1 + r1 + c);
+                        }
+                    } else {
+                        const int gy0 = uly + y0, gy1 = uly + y1;
+                        if (col_in && gy0 >= 0 && gy1 < sh) {
+                            if (pair_ok) {
+                                row_px2(img + (long long)gy0 * pitch, woff, bsh, p00, p01);
+                                row_px2(img + (long long)gy1 * pitch, woff, bsh, p10, p11);
+                            } else {
+                                image_px(img, pitch, gx0, gy0, p00); image_px(img, pitch, gx1, gy0, p01);
+                                image_px(img, pitch, gx0, gy1, p10); image_px(img, pitch, gx1, gy1, p11);
+                            }
+                        } else {
+                            canvas_px(img, pitch, sh, sw, d, x0, y0, p00);
+                            canvas_px(img, pitch, sh, sw, d, x1, y0, p01);
+                            canvas_px(img, pitch, sh, sw, d, x0, y1, p10);
+                            canvas_px(img, pitch, sh, sw, d, x1, y1, p11);
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float top = fmaf(p01[c], a1, p00[c] * a0), bot = fmaf(p11[c], a1, p10[c] * a0);
+                        float v = fmaf(bot, b1, top * b0);
+                        v = fminf(255.0f, fmaxf(0.0f, v * pn[c]));
+                        v3[c] = v * (1.0f / 255.0f);
+                    }
+                }
+                sp[0] = v3[0]; sp[kPlane] = v3[1]; sp[2 * kPlane] = v3[2];
+            }
+        }
+        __syncthreads();
+
+        // ---- stage T: torch bilinear from the rectangle (lane = output column, 4 rows per thread) --------------------
+        if (t_col) {
+            float* o = obase + (size_t)row0 * ow;
+#pragma unroll
+            for (int k = 0; k < kPasses; ++k, o += (size_t)kRowStep * ow) {
+                const int ly = wy + k * kRowStep;
+                if (ly >= nrow) break;
+                const int r0 = (s_oy0[row0 + ly] - ry_lo) * kPitchS, r1 = (s_oy1[row0 + ly] - ry_lo) * kPitchS;
+                const float ly1 = s_oly[row0 + ly], ly0 = __fsub_rn(1.0f, ly1);
+                const float* q00 = im + r0 + ox0;
+                const float* q01 = im + r0 + ox1;
+                const float* q10 = im + r1 + ox0;
+                const float* q11 = im + r1 + ox1;
+                float v[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    p00[c] = __ldg(r0 + 3 * x0 + c); p01[c] = __ldg(r0 + 3 * x1 + c);
-                    p10[c] = __ldg(r1 + 3 * x0 + c); p11[c] = __ldg(r1 + 3 * x1 + c);
+                    const float top = __fadd_rn(__fmul_rn(lx0, q00[c * kPlane]), __fmul_rn(lx1, q01[c * kPlane]));
+                    const float bot = __fadd_rn(__fmul_rn(lx0, q10[c * kPlane]), __fmul_rn(lx1, q11[c * kPlane]));
+                    v[c] = fmaf(__fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot)), na[c], nb[c]);
                 }
-            } else {
-                const int gx0 = d.ulx + x0, gx1 = d.ulx + x1, gy0 = d.uly + y0, gy1 = d.uly + y1;
-                if (gx0 >= 0 && gy0 >= 0 && gx1 < sw && gy1 < sh) {
-                    if (words && gx1 == gx0 + 1 && 3 * gx0 + 12 <= pitch) {
-                        image_px2(img, pitch, gx0, gy0, p00, p01); image_px2(img, pitch, gx0, gy1, p10, p11);
-                    } else {
-                        image_px(img, pitch, gx0, gy0, p00); image_px(img, pitch, gx1, gy0, p01);
-                        image_px(img, pitch, gx0, gy1, p10); image_px(img, pitch, gx1, gy1, p11);
-                    }
-                } else {
-                    canvas_px(img, pitch, sh, sw, d, x0, y0, p00);
-                    canvas_px(img, pitch, sh, sw, d, x1, y0, p01);
-                    canvas_px(img, pitch, sh, sw, d, x0, y1, p10);
-                    canvas_px(img, pitch, sh, sw, d, x1, y1, p11);
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float top = fmaf(p01[c], a1, p00[c] * a0), bot = fmaf(p11[c], a1, p10[c] * a0);
-                float v = fmaf(bot, b1, top * b0);
-                v = fminf(255.0f, fmaxf(0.0f, v * pn[c]));
-                v3[c] = v * (1.0f / 255.0f);
+                __stcs(o + c0 * plane, v[0]);
+                __stcs(o + plane, v[1]);
+                __stcs(o + c2 * plane, v[2]);
             }
         }
-        s_im[0][ly][lx] = v3[0]; s_im[1][ly][lx] = v3[1]; s_im[2][ly][lx] = v3[2];
-    }
-    __syncthreads();
-
-    // ---- stage T: torch bilinear from the rectangle (lane = output column, 4 rows per thread) ------------------------
-    const int lx = tid & 31;
-    if (lx >= ncol) return;
-    const int ox0 = s_ox0[lx] - rx_lo, ox1 = s_ox1[lx] - rx_lo;
-    const float lx1 = s_olx[lx], lx0 = __fsub_rn(1.0f, lx1);
-    const float na[3] = {na0, na1, na2}, nb[3] = {nb0, nb1, nb2};
-#pragma unroll
-    for (int k = 0; k < kFuseTile / (kFreiThreads / 32); ++k) {
-        const int ly = (tid >> 5) + k * (kFreiThreads / 32);
-        if (ly >= nrow) break;
-        const int oy0 = s_oy0[ly] - ry_lo, oy1 = s_oy1[ly] - ry_lo;
-        const float ly1 = s_oly[ly], ly0 = __fsub_rn(1.0f, ly1);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float top = __fadd_rn(__fmul_rn(lx0, s_im[c][oy0][ox0]), __fmul_rn(lx1, s_im[c][oy0][ox1]));
-            const float bot = __fadd_rn(__fmul_rn(lx0, s_im[c][oy1][ox0]), __fmul_rn(lx1, s_im[c][oy1][ox1]));
-            float v = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
-            v = fmaf(v, na[c], nb[c]);
-            const int co = (chan_order == LH_CHAN_BGR) ? 2 - c : c;
-            __stcs(dst + (((size_t)n * 3 + co) * oh + (ty0 + ly)) * ow + tx0 + lx, v);
-        }
+        if (kBufs == 1 && tile + 1 < kFuseTilesPerCta) __syncthreads();      // the next tile overwrites the rectangle
     }
 }
 
@@ -380,7 +449,7 @@ extern "C" int lh_frei_rgb_processing(const uint8_t* src, int64_t src_img_stride
         const int mw = max_rot_w, mh = max_rot_h;
         const int nz = rot_index ? n_rot : N;      // with the list only the rotated samples get CTAs
         if (nz > 0)
-            lh::frei_rotate_kernel<<<dim3((mw + lh::kFreiTileW - 1) / lh::kFreiTileW, (mh + lh::kFreiTileH - 1) / lh::kFreiTileH, nz),
+            lh::frei_rotate_kernel<<<dim3((mw + lh::kFreiTileW - 1) / lh::kFreiTileW, (mh + lh::kRotTileH - 1) / lh::kRotTileH, nz),
                                      lh::kFreiThreads, 0, st>>>(src, (long long)src_img_stride, src_h, src_w, src_pitch, desc,
                                                                 rot_index, scratch);
         LH_CHECK_LAUNCH();
@@ -434,7 +503,7 @@ extern "C" int lh_frei_fused(const uint8_t* src, int64_t src_img_stride, int src
         const int nz = rot_index ? n_rot : N;
         if (nz > 0)
             lh::frei_rotate_kernel<<<dim3((max_rot_w + lh::kFreiTileW - 1) / lh::kFreiTileW,
-                                          (max_rot_h + lh::kFreiTileH - 1) / lh::kFreiTileH, nz),
+                                          (max_rot_h + lh::kRotTileH - 1) / lh::kRotTileH, nz),
                                      lh::kFreiThreads, 0, st>>>(src, (long long)src_img_stride, src_h, src_w, src_pitch, desc,
                                                                 rot_index, scratch);
         LH_CHECK_LAUNCH();
@@ -443,7 +512,8 @@ extern "C" int lh_frei_fused(const uint8_t* src, int64_t src_img_stride, int src
     if (mean_std)
         for (int c = 0; c < 3; ++c) { a[c] = 1.0f / mean_std[3 + c]; b[c] = -mean_std[c] / mean_std[3 + c]; }
     const float sy = (float)res / (float)out_h, sx = (float)res / (float)out_w;     // ATen: float32 in / out
-    lh::frei_fused_kernel<<<dim3((out_w + lh::kFuseTile - 1) / lh::kFuseTile, (out_h + lh::kFuseTile - 1) / lh::kFuseTile, N),
+    constexpr int kCtaRows = lh::kFuseTile * lh::kFuseTilesPerCta;
+    lh::frei_fused_kernel<<<dim3((out_w + lh::kFuseTile - 1) / lh::kFuseTile, (out_h + kCtaRows - 1) / kCtaRows, N),
                             lh::kFreiThreads, 0, st>>>(src, (long long)src_img_stride, src_h, src_w, src_pitch, desc, scratch, res,
                                                        out, out_h, out_w, sy, sx, a[0], a[1], a[2], b[0], b[1], b[2], chan_order);
     LH_CHECK_LAUNCH();

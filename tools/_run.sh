@@ -1,3 +1,2 @@
-python tools/hm_time.py
-python -m pytest tests/test_gpu_kernels.py tests/test_gpu_pipeline.py tests/test_gpu_runner.py -x -q -m gpu 2>&1 | tail -2
-for w in C2 C3; do python bench.py --workload $w --steps 20 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); k=d['kernels']; print('$w', round(d['value']), round(d['ms_per_step']*1e3,1), 'serial', round(d['serial']['ms_per_step']*1e3,1), 'k1', round(k['warp_normalize']['ms']*1e3,1), 'fused', round(k['heatmap_fused']['ms']*1e3,1), 'alone', round(k['alone']['heatmap_fused_ms']*1e3,1))"; done
+python tools/frei_time.py
+python -m pytest tests/test_gpu_frei.py -x -q -m gpu 2>&1 | tail -2
