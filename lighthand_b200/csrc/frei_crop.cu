@@ -251,7 +251,8 @@ __global__ void __launch_bounds__(kFreiThreads) resize_f32_kernel(const float* _
 
 // ------------------------------------------------------------------------------------------------
 // Stages S + T in ONE kernel (round 2): the res x res float image of rgb_processing never goes to HBM.
-// CTA = a 32 x 32 tile of the final oh x ow output of one sample.  It works out which rectangle of the res x res
+// CTA = two vertically adjacent 32 x 32 tiles of the final oh x ow output of one sample (descriptor and column tables
+// are set up once, each tile has its own rectangle buffer so only one barrier separates its two stages).  Per tile it works out which rectangle of the res x res
 // intermediate the tile's torch-bilinear taps touch (<= 32 x 32 when res / out <= 0.9375: 224 -> 256 needs 30 x 30), renders
 // exactly that rectangle with stage S's arithmetic (cv2.resize in double coordinates, float32 blend, noise, clip, /255)
 // into shared memory, and resamples it with stage T's arithmetic (ATen's float32 operation order, one FMA normalises,
