@@ -261,11 +261,34 @@ __global__ void __launch_bounds__(kFreiThreads) resize_f32_kernel(const float* _
 // 256-image batch less HBM traffic (154 MB written + 154 MB read back) and one launch less.
 // ------------------------------------------------------------------------------------------------
 constexpr int kFuseTile = 32;
+
+// shared-memory load at a 32-bit shared address + compile-time byte offset (stage T reads 12 taps per output row off four
+// row/column sums; spelled out so that the adds are not redone per tap)
+template <int OFF>
+__device__ __forceinline__ float lds_off(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF));
+    return v;
+}
+// the value must live in a register from here on (keeps ptxas from re-deriving it from special registers and kernel
+// parameters at every use, which is what it does under the register cap)
+__device__ __forceinline__ void keep_reg(uint32_t& v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void keep_reg(int& v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void keep_reg(float*& v) { asm volatile("" : "+l"(v)); }
+__device__ __forceinline__ void keep_reg(const uint8_t*& v) { asm volatile("" : "+l"(v)); }
 constexpr int kFuseTilesPerCta = 2;      // vertically adjacent tiles per CTA: the column tables and the descriptor are set up once
 
 #ifndef LH_FREI_MINB
 #define LH_FREI_MINB 6
 #endif
+#ifndef LH_FREI_BUFS
+#define LH_FREI_BUFS 2
+#endif
+// one 16-byte record per rectangle row (stage S) and per output row (stage T): a single LDS.128 per row and stage instead
+// of four table reads with four address computations -- the kernel is instruction-bound (profiles/r02_frei_ncu_summary.txt)
+struct __align__(16) FuseSRow { int y0, y1; float b0, b1; };
+struct __align__(16) FuseTRow { int off0, off1; float l1, pad; };   // off = (tap row - rectangle top) * pitch, in bytes
+
 __global__ void __launch_bounds__(kFreiThreads, LH_FREI_MINB) frei_fused_kernel(const uint8_t* __restrict__ src, long long img_stride,
                                                                   int sh, int sw, int pitch,
                                                                   const lh_frei_desc* __restrict__ desc,
@@ -274,15 +297,16 @@ __global__ void __launch_bounds__(kFreiThreads, LH_FREI_MINB) frei_fused_kernel(
                                                                   float na0, float na1, float na2, float nb0, float nb1,
                                                                   float nb2, int chan_order) {
     constexpr int kRows = kFuseTile * kFuseTilesPerCta;
-#ifndef LH_FREI_BUFS
-#define LH_FREI_BUFS 2
-#endif
-    constexpr int kBufs = LH_FREI_BUFS;                                      // 1: a barrier between tiles; 2: one rectangle buffer per tile (7 CTAs / SM)
-    __shared__ float s_im[kBufs][3][kFuseTile][kFuseTile + 1];               // the rectangle of the intermediate image
+    constexpr int kBufs = LH_FREI_BUFS;                                      // 1: a barrier between tiles; 2: one rectangle buffer per tile
+    constexpr int kRowStep = kFreiThreads / 32, kPasses = kFuseTile / kRowStep;
+    constexpr int kPitchS = kFuseTile + 1, kPlane = kFuseTile * kPitchS;     // floats per rectangle row / channel plane
+    __shared__ float s_im[kBufs][3 * kPlane];                                // the rectangle of the intermediate image
+    __shared__ FuseSRow s_srow[kRows];
+    __shared__ FuseTRow s_trow[kRows];
     __shared__ int s_ox0[kFuseTile], s_ox1[kFuseTile], s_oy0[kRows], s_oy1[kRows];             // stage T taps (absolute)
     __shared__ float s_olx[kFuseTile], s_oly[kRows];
-    __shared__ int s_x0[kFuseTile], s_x1[kFuseTile], s_y0[kRows], s_y1[kRows];                 // stage S taps per rectangle column / row
-    __shared__ float s_a0[kFuseTile], s_a1[kFuseTile], s_b0[kRows], s_b1[kRows];
+    __shared__ int s_x0[kFuseTile], s_x1[kFuseTile];                                           // stage S taps per rectangle column
+    __shared__ float s_a0[kFuseTile], s_a1[kFuseTile];
 
     const int n = blockIdx.z;
     const lh_frei_desc& d = desc[n];
@@ -309,16 +333,29 @@ __global__ void __launch_bounds__(kFreiThreads, LH_FREI_MINB) frei_fused_kernel(
     // the rectangle of the intermediate image the taps touch: columns once, rows per tile (rw, rh <= 32: the launcher checks the scale)
     const int rx_lo = s_ox0[0], rw = s_ox1[ncol - 1] - rx_lo + 1;
 
-    // ---- stage S tables for the rectangles' columns / rows -----------------------------------------------------------
-    if (iw > 0 && ih > 0) {
-        if (tid < rw) {
+    // ---- stage S tables for the rectangles' columns / rows, stage T row records ------------------------------------
+    if (tid < kFuseTile) {
+        if (tid < rw && iw > 0 && ih > 0)
             cv2_linear_axis(rx_lo + tid, iw, d.scale_x, s_x0[tid], s_x1[tid], s_a0[tid], s_a1[tid]);
-        } else if (tid >= kFuseTile && tid < kFuseTile + kRows) {
-            const int t = tid - kFuseTile, tile = t / kFuseTile, r = t - tile * kFuseTile;
-            const int row0 = tile * kFuseTile, nr = min(kFuseTile, nrows - row0);
-            if (nr > 0) {
-                const int ry_lo = s_oy0[row0], rh = s_oy1[row0 + nr - 1] - ry_lo + 1;
-                if (r < rh) cv2_linear_axis(ry_lo + r, ih, d.scale_y, s_y0[t], s_y1[t], s_b0[t], s_b1[t]);
+    } else if (tid < kFuseTile + 2 * kRows) {
+        const bool is_t = tid >= kFuseTile + kRows;
+        const int t = tid - kFuseTile - (is_t ? kRows : 0), tile = t / kFuseTile, r = t - tile * kFuseTile;
+        const int row0 = tile * kFuseTile, nr = min(kFuseTile, nrows - row0);
+        if (nr > 0) {
+            const int ry_lo = s_oy0[row0];
+            if (is_t) {
+                if (r < nr) {
+                    FuseTRow tr;
+                    tr.off0 = (s_oy0[t] - ry_lo) * kPitchS * 4; tr.off1 = (s_oy1[t] - ry_lo) * kPitchS * 4; tr.l1 = s_oly[t]; tr.pad = 0.f;
+                    s_trow[t] = tr;
+                }
+            } else if (iw > 0 && ih > 0) {
+                const int rh = s_oy1[row0 + nr - 1] - ry_lo + 1;
+                if (r < rh) {
+                    FuseSRow sr;
+                    cv2_linear_axis(ry_lo + r, ih, d.scale_y, sr.y0, sr.y1, sr.b0, sr.b1);
+                    s_srow[t] = sr;
+                }
             }
         }
     }
@@ -327,11 +364,8 @@ __global__ void __launch_bounds__(kFreiThreads, LH_FREI_MINB) frei_fused_kernel(
     const uint8_t* img = src + (long long)n * img_stride;
     const bool words = ((reinterpret_cast<uintptr_t>(img) | (uintptr_t)pitch) & 3u) == 0;      // uniform
     const float pn[3] = {d.pn[0], d.pn[1], d.pn[2]};
-    const float na[3] = {na0, na1, na2}, nb[3] = {nb0, nb1, nb2};
     const int ulx = d.ulx, uly = d.uly;
     const int lx = tid & 31, wy = tid >> 5;
-    constexpr int kRowStep = kFreiThreads / 32, kPasses = kFuseTile / kRowStep;
-    constexpr int kPitchS = kFuseTile + 1, kPlane = kFuseTile * kPitchS;       // floats per rectangle row / channel plane
     // this lane's rectangle column (stage S) and output column (stage T): the same for every tile of the CTA
     const bool s_col = lx < rw && iw > 0 && ih > 0;
     const int x0 = s_col ? s_x0[lx] : 0, x1 = s_col ? s_x1[lx] : 0;
@@ -339,63 +373,69 @@ __global__ void __launch_bounds__(kFreiThreads, LH_FREI_MINB) frei_fused_kernel(
     const int gx0 = ulx + x0, gx1 = ulx + x1;
     const bool col_in = gx0 >= 0 && gx1 < sw;
     const bool pair_ok = words && col_in && gx1 == gx0 + 1 && 3 * gx0 + 12 <= pitch;
-    const unsigned boff = (unsigned)(3 * gx0), woff = boff & ~3u, bsh = boff << 3;
+    const unsigned boff = (unsigned)(3 * gx0);
+    unsigned bsh = boff << 3;
+    const uint8_t* imgw = img + (pair_ok ? (boff & ~3u) : 0u);                 // this column's first word of image row 0
+    keep_reg(imgw); keep_reg(bsh);
     const float* rot0 = rotated ? scratch + d.scratch_off + 3 * x0 : nullptr;  // rotated canvas: this column's two taps
     const float* rot1 = rotated ? scratch + d.scratch_off + 3 * x1 : nullptr;
     const bool t_col = lx < ncol;
     const int ox0 = t_col ? s_ox0[lx] - rx_lo : 0, ox1 = t_col ? s_ox1[lx] - rx_lo : 0;
     const float lx1 = t_col ? s_olx[lx] : 0.f, lx0 = __fsub_rn(1.0f, lx1);
-    const size_t plane = (size_t)oh * ow;
-    const int c0 = (chan_order == LH_CHAN_BGR) ? 2 : 0, c2 = 2 - c0;           // output plane of channels 0 and 2
-    float* const obase = dst + (size_t)n * 3 * plane + (size_t)(ty0 + wy) * ow + tx0 + lx;
+    // 32-bit indexing inside the sample's three output planes (the launcher checks 3 * oh * ow < 2^31)
+    const int plane = oh * ow;
+    const int c0 = (chan_order == LH_CHAN_BGR) ? 2 * plane : 0, c2 = 2 * plane - c0;   // plane offsets of channels 0 and 2
+    float* const osample = dst + (size_t)n * 3 * (size_t)plane;
+    int ofirst = (ty0 + wy) * ow + tx0 + lx;
+    float* osample_k = osample;
+    keep_reg(osample_k); keep_reg(ofirst);
 
 #pragma unroll 1
     for (int tile = 0; tile < kFuseTilesPerCta; ++tile) {
         const int row0 = tile * kFuseTile, nrow = min(kFuseTile, nrows - row0);
         if (nrow <= 0) break;                                                                   // uniform
-        const int ry_lo = s_oy0[row0], rh = s_oy1[row0 + nrow - 1] - ry_lo + 1;
-        float* const im = &s_im[tile % kBufs][0][0][0];
+        const int rh = s_oy1[row0 + nrow - 1] - s_oy0[row0] + 1;
+        float* const im = s_im[tile % kBufs];
 
         // ---- stage S: the rectangle of rgb_processing's image into shared memory (lane = column, 8 rows per pass) ---
         if (lx < rw) {
             float* sp = im + wy * kPitchS + lx;
+            const FuseSRow* srp = s_srow + row0 + wy;
 #pragma unroll
-            for (int k = 0; k < kPasses; ++k, sp += kRowStep * kPitchS) {
-                const int ly = wy + k * kRowStep;
-                if (ly >= rh) break;
+            for (int k = 0; k < kPasses; ++k, sp += kRowStep * kPitchS, srp += kRowStep) {
+                if (wy + k * kRowStep >= rh) break;
                 float v3[3] = {0.f, 0.f, 0.f};
                 if (s_col) {
-                    const int y0 = s_y0[row0 + ly], y1 = s_y1[row0 + ly];
-                    const float b0 = s_b0[row0 + ly], b1 = s_b1[row0 + ly];
+                    const FuseSRow sr = *srp;
                     float p00[3], p01[3], p10[3], p11[3];
                     if (rotated) {
-                        const size_t r0 = (size_t)y0 * iw * 3, r1 = (size_t)y1 * iw * 3;
+                        const unsigned r0 = (unsigned)(sr.y0 * iw * 3), r1 = (unsigned)(sr.y1 * iw * 3);
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
                             p00[c] = __ldg(rot0 + r0 + c); p01[c] = __ldg(rot1 + r0 + c);
                             p10[c] = __ldg(rot0 + r1 + c); p11[c] = __ldg(rot1 + r1 + c);
                         }
                     } else {
-                        const int gy0 = uly + y0, gy1 = uly + y1;
+                        const int gy0 = uly + sr.y0, gy1 = uly + sr.y1;
                         if (col_in && gy0 >= 0 && gy1 < sh) {
                             if (pair_ok) {
-                                row_px2(img + (long long)gy0 * pitch, woff, bsh, p00, p01);
-                                row_px2(img + (long long)gy1 * pitch, woff, bsh, p10, p11);
+                                row_px2(imgw + (unsigned)(gy0 * pitch), 0u, bsh, p00, p01);
+                                row_px2(imgw + (unsigned)(gy1 * pitch), 0u, bsh, p10, p11);
                             } else {
                                 image_px(img, pitch, gx0, gy0, p00); image_px(img, pitch, gx1, gy0, p01);
                                 image_px(img, pitch, gx0, gy1, p10); image_px(img, pitch, gx1, gy1, p11);
                             }
                         } else {
-                            canvas_px(img, pitch, sh, sw, d, x0, y0, p00);
-                            canvas_px(img, pitch, sh, sw, d, x1, y0, p01);
-                            canvas_px(img, pitch, sh, sw, d, x0, y1, p10);
-                            canvas_px(img, pitch, sh, sw, d, x1, y1, p11);
+                            canvas_px(img, pitch, sh, sw, d, x0, sr.y0, p00);
+                            canvas_px(img, pitch, sh, sw, d, x1, sr.y0, p01);
+                            canvas_px(img, pitch, sh, sw, d, x0, sr.y1, p10);
+                            canvas_px(img, pitch, sh, sw, d, x1, sr.y1, p11);
                         }
                     }
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         const float top = fmaf(p01[c], a1, p00[c] * a0), bot = fmaf(p11[c], a1, p10[c] * a0);
-                        float v = fmaf(bot, b1, top * b0);
+                        float v = fmaf(bot, sr.b1, top * sr.b0);
                         v = fminf(255.0f, fmaxf(0.0f, v * pn[c]));
                         v3[c] = v * (1.0f / 255.0f);
                     }
@@ -407,27 +447,31 @@ __global__ void __launch_bounds__(kFreiThreads, LH_FREI_MINB) frei_fused_kernel(
 
         // ---- stage T: torch bilinear from the rectangle (lane = output column, 4 rows per thread) --------------------
         if (t_col) {
-            float* o = obase + (size_t)row0 * ow;
+            const uint32_t imb = smem_u32(im);
+            uint32_t qa = imb + 4u * (unsigned)ox0, qb = imb + 4u * (unsigned)ox1;
+            keep_reg(qa); keep_reg(qb);
+            const FuseTRow* trp = s_trow + row0 + wy;
+            int oi = ofirst + row0 * ow;
 #pragma unroll
-            for (int k = 0; k < kPasses; ++k, o += (size_t)kRowStep * ow) {
-                const int ly = wy + k * kRowStep;
-                if (ly >= nrow) break;
-                const int r0 = (s_oy0[row0 + ly] - ry_lo) * kPitchS, r1 = (s_oy1[row0 + ly] - ry_lo) * kPitchS;
-                const float ly1 = s_oly[row0 + ly], ly0 = __fsub_rn(1.0f, ly1);
-                const float* q00 = im + r0 + ox0;
-                const float* q01 = im + r0 + ox1;
-                const float* q10 = im + r1 + ox0;
-                const float* q11 = im + r1 + ox1;
-                float v[3];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float top = __fadd_rn(__fmul_rn(lx0, q00[c * kPlane]), __fmul_rn(lx1, q01[c * kPlane]));
-                    const float bot = __fadd_rn(__fmul_rn(lx0, q10[c * kPlane]), __fmul_rn(lx1, q11[c * kPlane]));
-                    v[c] = fmaf(__fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot)), na[c], nb[c]);
-                }
-                __stcs(o + c0 * plane, v[0]);
-                __stcs(o + plane, v[1]);
-                __stcs(o + c2 * plane, v[2]);
+            for (int k = 0; k < kPasses; ++k, trp += kRowStep, oi += kRowStep * ow) {
+                if (wy + k * kRowStep >= nrow) break;
+                const FuseTRow tr = *trp;
+                const float ly1 = tr.l1, ly0 = __fsub_rn(1.0f, ly1);
+                const uint32_t q00 = qa + (unsigned)tr.off0, q01 = qb + (unsigned)tr.off0;      // off: bytes
+                const uint32_t q10 = qa + (unsigned)tr.off1, q11 = qb + (unsigned)tr.off1;
+                constexpr int P = kPlane * 4;
+                const float t0 = __fadd_rn(__fmul_rn(lx0, lds_off<0>(q00)), __fmul_rn(lx1, lds_off<0>(q01)));
+                const float b0 = __fadd_rn(__fmul_rn(lx0, lds_off<0>(q10)), __fmul_rn(lx1, lds_off<0>(q11)));
+                const float t1 = __fadd_rn(__fmul_rn(lx0, lds_off<P>(q00)), __fmul_rn(lx1, lds_off<P>(q01)));
+                const float b1 = __fadd_rn(__fmul_rn(lx0, lds_off<P>(q10)), __fmul_rn(lx1, lds_off<P>(q11)));
+                const float t2 = __fadd_rn(__fmul_rn(lx0, lds_off<2 * P>(q00)), __fmul_rn(lx1, lds_off<2 * P>(q01)));
+                const float b2 = __fadd_rn(__fmul_rn(lx0, lds_off<2 * P>(q10)), __fmul_rn(lx1, lds_off<2 * P>(q11)));
+                const float v0 = fmaf(__fadd_rn(__fmul_rn(ly0, t0), __fmul_rn(ly1, b0)), na0, nb0);
+                const float v1 = fmaf(__fadd_rn(__fmul_rn(ly0, t1), __fmul_rn(ly1, b1)), na1, nb1);
+                const float v2 = fmaf(__fadd_rn(__fmul_rn(ly0, t2), __fmul_rn(ly1, b2)), na2, nb2);
+                __stcs(osample_k + (oi + c0), v0);
+                __stcs(osample_k + (oi + plane), v1);
+                __stcs(osample_k + (oi + c2), v2);
             }
         }
         if (kBufs == 1 && tile + 1 < kFuseTilesPerCta) __syncthreads();      // the next tile overwrites the rectangle
@@ -499,6 +543,7 @@ extern "C" int lh_frei_fused(const uint8_t* src, int64_t src_img_stride, int src
     if (!src || !desc || !out || (max_rot_w > 0 && !scratch)) return LH_ENULL;
     if (N > 65535 || res > 32768 || max_rot_w > 32768 || max_rot_h > 32768) return LH_EINVAL;
     if (32.0 * res / out_w + 2.0 > lh::kFuseTile || 32.0 * res / out_h + 2.0 > lh::kFuseTile) return LH_EUNSUPPORTED;
+    if ((int64_t)3 * out_h * out_w >= ((int64_t)1 << 31) || (int64_t)src_h * src_pitch >= ((int64_t)1 << 31)) return LH_EUNSUPPORTED;   // 32-bit in-sample offsets
     cudaStream_t st = (cudaStream_t)stream;
     if (max_rot_w > 0) {
         const int nz = rot_index ? n_rot : N;
