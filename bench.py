@@ -297,6 +297,7 @@ def jpeg_leg(hp, host_sets, B, S, Ke, args):
     outs = [hp.new_outputs(), hp.new_outputs()]
     res = {"h2d_bytes_per_step": nbytes + B * 48 + B + B * 21 * 8, "jpeg_quality": 90, "image_bytes_mean": nbytes / B,
            "raw_bytes_per_image": S * S * 3, "data": "synthetic natural-like images (smooth colour field + edges + noise), 4:2:0"}
+    # every backend this part offers is timed; the line carries the fastest one and lists the others
     for backend in ("hardware", "gpu_hybrid", "hybrid"):
         try:
             def run(n_steps):
@@ -315,9 +316,10 @@ def jpeg_leg(hp, host_sets, B, S, Ke, args):
             run(n_steps)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
-            res.update({"value": B * n_steps / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / n_steps, "steps": n_steps,
-                        "backend": backend})
-            break
+            res.setdefault("backends", {})[backend] = {"value": B * n_steps / dt, "ms_per_step": 1e3 * dt / n_steps}
+            if "value" not in res or B * n_steps / dt > res["value"]:
+                res.update({"value": B * n_steps / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / n_steps, "steps": n_steps,
+                            "backend": backend})
         except Exception as ex:          # backend not available on this part: try the next one
             res.setdefault("backends_unavailable", []).append(f"{backend}: {type(ex).__name__}")
     return res
