@@ -321,6 +321,9 @@ int lh_color_jitter_normalize(const float* src, const lh_jitter_params* params, 
  * Decoder = nvJPEG, bound at run time; not bit-identical to libjpeg-turbo (IDCT / chroma upsampling accuracy is not
  * part of the JPEG standard): the tolerance is stated in DESIGN.md and tested in tests/test_gpu_jpeg.py.
  * backend: nvJPEG's (DEFAULT, HYBRID = Huffman on the CPU, GPU_HYBRID = Huffman on the GPU, HARDWARE = the NVJPG engine).
+ * cpu_threads: with HYBRID and cpu_threads > 1 the host Huffman stage runs on that many worker threads (nvJPEG's decoupled
+ * API, one decoder state per thread, images handed out dynamically; the call returns when the batch is decoded); ignored
+ * by the other backends.  The pixels do not depend on the thread count.
  * Every bit-stream of a batch must have the size w x h (else LH_EINVAL).  The data / sizes arrays and the bit-streams
  * must stay valid until the stream has passed the call.
  * ------------------------------------------------------------------------------------------ */

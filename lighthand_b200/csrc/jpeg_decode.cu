@@ -15,8 +15,11 @@
 #include <dlfcn.h>
 #include <nvjpeg.h>
 
+#include <atomic>
+#include <condition_variable>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "lh_common.cuh"
@@ -31,6 +34,25 @@ struct JpegApi {
     nvjpegStatus_t (*GetImageInfo)(nvjpegHandle_t, const unsigned char*, size_t, int*, nvjpegChromaSubsampling_t*, int*, int*) = nullptr;
     nvjpegStatus_t (*BatchedInit)(nvjpegHandle_t, nvjpegJpegState_t, int, int, nvjpegOutputFormat_t) = nullptr;
     nvjpegStatus_t (*Batched)(nvjpegHandle_t, nvjpegJpegState_t, const unsigned char* const*, const size_t*, nvjpegImage_t*, cudaStream_t) = nullptr;
+    // decoupled API (host Huffman stage per image, callable from several threads with their own states)
+    nvjpegStatus_t (*DecoderCreate)(nvjpegHandle_t, nvjpegBackend_t, nvjpegJpegDecoder_t*) = nullptr;
+    nvjpegStatus_t (*DecoderDestroy)(nvjpegJpegDecoder_t) = nullptr;
+    nvjpegStatus_t (*DecoderStateCreate)(nvjpegHandle_t, nvjpegJpegDecoder_t, nvjpegJpegState_t*) = nullptr;
+    nvjpegStatus_t (*PinnedCreate)(nvjpegHandle_t, nvjpegPinnedAllocator_t*, nvjpegBufferPinned_t*) = nullptr;
+    nvjpegStatus_t (*PinnedDestroy)(nvjpegBufferPinned_t) = nullptr;
+    nvjpegStatus_t (*DeviceCreate)(nvjpegHandle_t, nvjpegDevAllocator_t*, nvjpegBufferDevice_t*) = nullptr;
+    nvjpegStatus_t (*DeviceDestroy)(nvjpegBufferDevice_t) = nullptr;
+    nvjpegStatus_t (*AttachPinned)(nvjpegJpegState_t, nvjpegBufferPinned_t) = nullptr;
+    nvjpegStatus_t (*AttachDevice)(nvjpegJpegState_t, nvjpegBufferDevice_t) = nullptr;
+    nvjpegStatus_t (*StreamCreate)(nvjpegHandle_t, nvjpegJpegStream_t*) = nullptr;
+    nvjpegStatus_t (*StreamDestroy)(nvjpegJpegStream_t) = nullptr;
+    nvjpegStatus_t (*StreamParse)(nvjpegHandle_t, const unsigned char*, size_t, int, int, nvjpegJpegStream_t) = nullptr;
+    nvjpegStatus_t (*ParamsCreate)(nvjpegHandle_t, nvjpegDecodeParams_t*) = nullptr;
+    nvjpegStatus_t (*ParamsDestroy)(nvjpegDecodeParams_t) = nullptr;
+    nvjpegStatus_t (*ParamsSetOutputFormat)(nvjpegDecodeParams_t, nvjpegOutputFormat_t) = nullptr;
+    nvjpegStatus_t (*DecodeHost)(nvjpegHandle_t, nvjpegJpegDecoder_t, nvjpegJpegState_t, nvjpegDecodeParams_t, nvjpegJpegStream_t) = nullptr;
+    nvjpegStatus_t (*DecodeTransfer)(nvjpegHandle_t, nvjpegJpegDecoder_t, nvjpegJpegState_t, nvjpegJpegStream_t, cudaStream_t) = nullptr;
+    nvjpegStatus_t (*DecodeDevice)(nvjpegHandle_t, nvjpegJpegDecoder_t, nvjpegJpegState_t, nvjpegImage_t*, cudaStream_t) = nullptr;
     bool ok = false;
 };
 
@@ -51,6 +73,19 @@ const JpegApi& jpeg_api() {
         api.GetImageInfo = reinterpret_cast<decltype(api.GetImageInfo)>(sym("nvjpegGetImageInfo"));
         api.BatchedInit = reinterpret_cast<decltype(api.BatchedInit)>(sym("nvjpegDecodeBatchedInitialize"));
         api.Batched = reinterpret_cast<decltype(api.Batched)>(sym("nvjpegDecodeBatched"));
+#define LH_JSYM(field, name) api.field = reinterpret_cast<decltype(api.field)>(sym(name))
+        LH_JSYM(DecoderCreate, "nvjpegDecoderCreate");          LH_JSYM(DecoderDestroy, "nvjpegDecoderDestroy");
+        LH_JSYM(DecoderStateCreate, "nvjpegDecoderStateCreate");
+        LH_JSYM(PinnedCreate, "nvjpegBufferPinnedCreate");      LH_JSYM(PinnedDestroy, "nvjpegBufferPinnedDestroy");
+        LH_JSYM(DeviceCreate, "nvjpegBufferDeviceCreate");      LH_JSYM(DeviceDestroy, "nvjpegBufferDeviceDestroy");
+        LH_JSYM(AttachPinned, "nvjpegStateAttachPinnedBuffer"); LH_JSYM(AttachDevice, "nvjpegStateAttachDeviceBuffer");
+        LH_JSYM(StreamCreate, "nvjpegJpegStreamCreate");        LH_JSYM(StreamDestroy, "nvjpegJpegStreamDestroy");
+        LH_JSYM(StreamParse, "nvjpegJpegStreamParse");
+        LH_JSYM(ParamsCreate, "nvjpegDecodeParamsCreate");      LH_JSYM(ParamsDestroy, "nvjpegDecodeParamsDestroy");
+        LH_JSYM(ParamsSetOutputFormat, "nvjpegDecodeParamsSetOutputFormat");
+        LH_JSYM(DecodeHost, "nvjpegDecodeJpegHost");            LH_JSYM(DecodeTransfer, "nvjpegDecodeJpegTransferToDevice");
+        LH_JSYM(DecodeDevice, "nvjpegDecodeJpegDevice");
+#undef LH_JSYM
         api.ok = all;
     });
     return api;
@@ -58,19 +93,152 @@ const JpegApi& jpeg_api() {
 
 }  // namespace
 
+// One host thread of the threaded HYBRID mode: its own decoder, two (state, bit-stream, pinned + device buffer) sets so
+// that the Huffman decode of its next image runs while the device stage of the previous one is in flight, one stream.
+struct JpegWorker {
+    nvjpegJpegDecoder_t decoder = nullptr;
+    nvjpegDecodeParams_t params = nullptr;
+    nvjpegJpegState_t state[2] = {nullptr, nullptr};
+    nvjpegJpegStream_t jstream[2] = {nullptr, nullptr};
+    nvjpegBufferPinned_t pinned[2] = {nullptr, nullptr};
+    nvjpegBufferDevice_t devbuf[2] = {nullptr, nullptr};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    bool used[2] = {false, false};
+    std::thread thread;
+};
+
+// the batch a threaded decode call hands to the workers
+struct JpegJob {
+    const uint8_t* const* data = nullptr;
+    const size_t* sizes = nullptr;
+    int n = 0, dst_pitch = 0, w = 0, h = 0;
+    uint8_t* dst = nullptr;
+    int64_t dst_img_stride = 0;
+    cudaEvent_t start = nullptr;        // recorded on the caller's stream at entry: dst may still be read before it
+};
+
 struct lh_jpeg {
     int device = 0, backend = 0, cpu_threads = 1;
     nvjpegHandle_t handle = nullptr;
     nvjpegJpegState_t state = nullptr;
     int init_batch = 0;                 // batch size nvjpegDecodeBatchedInitialize was last called with
     std::vector<nvjpegImage_t> outs;
+    // threaded HYBRID mode (backend == LH_JPEG_BACKEND_HYBRID && cpu_threads > 1)
+    std::vector<JpegWorker*> workers;
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    uint64_t generation = 0;            // bumped per batch; workers wait for a new one
+    int running = 0;                    // workers still busy with the current batch
+    bool quit = false;
+    JpegJob job;
+    std::atomic<int> next{0};           // next image index (dynamic distribution)
+    std::atomic<int> failed{0}, bad_input{0};   // decode errors / null or wrongly sized bit-streams
+    cudaEvent_t ev_start = nullptr;
 };
+
+namespace {
+
+void worker_free(const JpegApi& a, JpegWorker* w) {
+    for (int k = 0; k < 2; ++k) {
+        if (w->ev[k]) cudaEventDestroy(w->ev[k]);
+        if (w->state[k]) a.StateDestroy(w->state[k]);
+        if (w->jstream[k]) a.StreamDestroy(w->jstream[k]);
+        if (w->pinned[k]) a.PinnedDestroy(w->pinned[k]);
+        if (w->devbuf[k]) a.DeviceDestroy(w->devbuf[k]);
+    }
+    if (w->params) a.ParamsDestroy(w->params);
+    if (w->decoder) a.DecoderDestroy(w->decoder);
+    if (w->stream) cudaStreamDestroy(w->stream);
+    delete w;
+}
+
+bool worker_setup(const JpegApi& a, lh_jpeg* j, JpegWorker* w) {
+    const nvjpegStatus_t ok = NVJPEG_STATUS_SUCCESS;
+    if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (a.DecoderCreate(j->handle, NVJPEG_BACKEND_HYBRID, &w->decoder) != ok) return false;
+    if (a.ParamsCreate(j->handle, &w->params) != ok) return false;
+    if (a.ParamsSetOutputFormat(w->params, NVJPEG_OUTPUT_RGBI) != ok) return false;
+    for (int k = 0; k < 2; ++k) {
+        if (cudaEventCreateWithFlags(&w->ev[k], cudaEventDisableTiming) != cudaSuccess) return false;
+        if (a.DecoderStateCreate(j->handle, w->decoder, &w->state[k]) != ok) return false;
+        if (a.StreamCreate(j->handle, &w->jstream[k]) != ok) return false;
+        if (a.PinnedCreate(j->handle, nullptr, &w->pinned[k]) != ok) return false;
+        if (a.DeviceCreate(j->handle, nullptr, &w->devbuf[k]) != ok) return false;
+        if (a.AttachPinned(w->state[k], w->pinned[k]) != ok) return false;
+        if (a.AttachDevice(w->state[k], w->devbuf[k]) != ok) return false;
+    }
+    return true;
+}
+
+// body of one worker thread: per batch, take image indices until none is left
+void worker_main(lh_jpeg* j, JpegWorker* w) {
+    const JpegApi& a = jpeg_api();
+    cudaSetDevice(j->device);
+    uint64_t seen = 0;
+    for (;;) {
+        {
+            std::unique_lock<std::mutex> lk(j->mu);
+            j->cv_go.wait(lk, [&] { return j->quit || j->generation != seen; });
+            if (j->quit) return;
+            seen = j->generation;
+        }
+        const JpegJob job = j->job;
+        bool bad = cudaStreamWaitEvent(w->stream, job.start, 0) != cudaSuccess;
+        int k = 0;
+        for (int i; !bad && (i = j->next.fetch_add(1)) < job.n; k ^= 1) {
+            if (w->used[k] && cudaEventSynchronize(w->ev[k]) != cudaSuccess) { bad = true; break; }   // the set is free again
+            {   // one batch = one tensor: every bit-stream must be w x h
+                int comps = 0, ws[NVJPEG_MAX_COMPONENT], hs[NVJPEG_MAX_COMPONENT];
+                nvjpegChromaSubsampling_t ss;
+                if (!job.data[i] || !job.sizes[i]) { j->bad_input.store(LH_ENULL); break; }
+                if (a.GetImageInfo(j->handle, job.data[i], job.sizes[i], &comps, &ss, ws, hs) != NVJPEG_STATUS_SUCCESS) { bad = true; break; }
+                if (ws[0] != job.w || hs[0] != job.h) { j->bad_input.store(LH_EINVAL); break; }
+            }
+            nvjpegImage_t out{};
+            out.channel[0] = job.dst + (int64_t)i * job.dst_img_stride;
+            out.pitch[0] = (size_t)job.dst_pitch;
+            bad = a.StreamParse(j->handle, job.data[i], job.sizes[i], 0, 0, w->jstream[k]) != NVJPEG_STATUS_SUCCESS ||
+                  a.DecodeHost(j->handle, w->decoder, w->state[k], w->params, w->jstream[k]) != NVJPEG_STATUS_SUCCESS ||
+                  a.DecodeTransfer(j->handle, w->decoder, w->state[k], w->jstream[k], w->stream) != NVJPEG_STATUS_SUCCESS ||
+                  a.DecodeDevice(j->handle, w->decoder, w->state[k], &out, w->stream) != NVJPEG_STATUS_SUCCESS ||
+                  cudaEventRecord(w->ev[k], w->stream) != cudaSuccess;
+            w->used[k] = true;
+        }
+        // everything this worker issued is complete when the call returns: the caller's bit-streams may go away
+        if (cudaStreamSynchronize(w->stream) != cudaSuccess) bad = true;
+        w->used[0] = w->used[1] = false;
+        if (bad) j->failed.fetch_add(1);
+        {
+            std::lock_guard<std::mutex> lk(j->mu);
+            if (--j->running == 0) j->cv_done.notify_all();
+        }
+    }
+}
+
+void workers_stop(lh_jpeg* j) {
+    {
+        std::lock_guard<std::mutex> lk(j->mu);
+        j->quit = true;
+    }
+    j->cv_go.notify_all();
+    const JpegApi& a = jpeg_api();
+    for (JpegWorker* w : j->workers) {
+        if (w->thread.joinable()) w->thread.join();
+        worker_free(a, w);
+    }
+    j->workers.clear();
+}
+
+}  // namespace
 
 extern "C" void lh_jpeg_destroy(lh_jpeg* j) {
     if (!j) return;
     const JpegApi& a = jpeg_api();
     if (a.ok) {
         cudaSetDevice(j->device);
+        workers_stop(j);
+        if (j->ev_start) cudaEventDestroy(j->ev_start);
         if (j->state) a.StateDestroy(j->state);
         if (j->handle) a.Destroy(j->handle);
     }
@@ -94,6 +262,17 @@ extern "C" int lh_jpeg_create(int device, int backend, int cpu_threads, lh_jpeg*
         lh_jpeg_destroy(j);
         return LH_EJPEG;                // e.g. LH_JPEG_BACKEND_HARDWARE on a part / driver without the engine
     }
+    if (backend == LH_JPEG_BACKEND_HYBRID && cpu_threads > 1) {
+        // threaded HYBRID mode: the Huffman stage is host work, one image at a time -- spread it over cpu_threads threads
+        if (cudaEventCreateWithFlags(&j->ev_start, cudaEventDisableTiming) != cudaSuccess) { lh_jpeg_destroy(j); return LH_EJPEG; }
+        for (int t = 0; t < cpu_threads; ++t) {
+            JpegWorker* w = new (std::nothrow) JpegWorker();
+            if (!w) { lh_jpeg_destroy(j); return LH_ENOMEM; }
+            j->workers.push_back(w);
+            if (!worker_setup(a, j, w)) { lh_jpeg_destroy(j); return LH_EJPEG; }
+        }
+        for (JpegWorker* w : j->workers) w->thread = std::thread(worker_main, j, w);
+    }
     *out = j;
     return LH_OK;
 }
@@ -107,13 +286,33 @@ extern "C" int lh_jpeg_decode_batch(lh_jpeg* j, const uint8_t* const* data, cons
     if (!a.ok) return LH_EJPEG;
     cudaError_t e = cudaSetDevice(j->device);
     if (e != cudaSuccess) return (int)e;
-    // every bit-stream must decode to w x h x 3 (one batch = one tensor)
-    for (int i = 0; i < n; ++i) {
+    // every bit-stream must decode to w x h x 3 (one batch = one tensor); the threaded mode checks inside its workers
+    for (int i = 0; i < n && j->workers.empty(); ++i) {
         if (!data[i] || !sizes[i]) return LH_ENULL;
         int comps = 0, ws[NVJPEG_MAX_COMPONENT], hs[NVJPEG_MAX_COMPONENT];
         nvjpegChromaSubsampling_t ss;
         if (a.GetImageInfo(j->handle, data[i], sizes[i], &comps, &ss, ws, hs) != NVJPEG_STATUS_SUCCESS) return LH_EJPEG;
         if (ws[0] != w || hs[0] != h) return LH_EINVAL;
+    }
+    if (!j->workers.empty()) {
+        if (cudaEventRecord(j->ev_start, (cudaStream_t)stream) != cudaSuccess) return LH_EJPEG;
+        {
+            std::lock_guard<std::mutex> lk(j->mu);
+            j->job.data = data; j->job.sizes = sizes; j->job.n = n; j->job.dst = dst;
+            j->job.dst_img_stride = dst_img_stride; j->job.dst_pitch = dst_pitch; j->job.start = j->ev_start;
+            j->job.w = w; j->job.h = h;
+            j->next.store(0); j->failed.store(0); j->bad_input.store(0);
+            j->running = (int)j->workers.size();
+            ++j->generation;
+        }
+        j->cv_go.notify_all();
+        {
+            std::unique_lock<std::mutex> lk(j->mu);
+            j->cv_done.wait(lk, [&] { return j->running == 0; });
+        }
+        // the worker streams were synchronised: the images are in place, whatever `stream` does next sees them
+        if (j->bad_input.load()) return j->bad_input.load();
+        return j->failed.load() ? LH_EJPEG : LH_OK;
     }
     if (j->init_batch != n) {
         if (a.BatchedInit(j->handle, j->state, n, j->cpu_threads, NVJPEG_OUTPUT_RGBI) != NVJPEG_STATUS_SUCCESS) return LH_EJPEG;

@@ -14,6 +14,8 @@
 #include <cstring>
 #include <new>
 
+#include <thread>
+
 #include "lh_common.cuh"
 
 namespace {
@@ -233,7 +235,14 @@ extern "C" int lh_pipeline_submit_inputs_jpeg(lh_pipeline* p, const uint8_t* con
         p->jpeg = nullptr;
     }
     if (!p->jpeg) {
-        const int rc = lh_jpeg_create(p->cfg.device, jpeg_backend, 1, &p->jpeg);
+        // HYBRID decodes the entropy-coded data on the host: give it the host's cores (LH_JPEG_THREADS overrides, at most 32)
+        int threads = 1;
+        if (jpeg_backend == LH_JPEG_BACKEND_HYBRID) {
+            const char* e = getenv("LH_JPEG_THREADS");
+            threads = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+            threads = threads < 1 ? 1 : (threads > 32 ? 32 : threads);
+        }
+        const int rc = lh_jpeg_create(p->cfg.device, jpeg_backend, threads, &p->jpeg);
         if (rc) return rc;
         p->jpeg_backend = jpeg_backend;
     }

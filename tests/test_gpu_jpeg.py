@@ -56,6 +56,26 @@ def test_decode_batch_vs_reference_reader(tmp_path, backend):
     dec.close()
 
 
+def test_threaded_hybrid_equals_single_threaded(tmp_path):
+    """cpu_threads > 1 spreads the host Huffman stage of the HYBRID backend over worker threads (decoupled nvJPEG API, one
+    state per thread); same decoder, so the pixels must not change -- also with fewer images than threads and across batches."""
+    from lighthand_b200.utils.tsv_file import JpegDecoder, TSVFile, decode_batch
+    for ext in (".tsv", ".lineidx"):
+        shutil.copy(os.path.join(GOLD, "frei_store" + ext), tmp_path / ("frei_store" + ext))
+    tsv = TSVFile(str(tmp_path / "frei_store.tsv"))
+    one = JpegDecoder(backend="hybrid", cpu_threads=1)
+    many = JpegDecoder(backend="hybrid", cpu_threads=6)
+    idx = list(range(len(tsv))) * 3
+    want = decode_batch(tsv, idx, (64, 64), one)
+    for _ in range(3):
+        got = decode_batch(tsv, idx, (64, 64), many)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want)
+    assert torch.equal(decode_batch(tsv, [5, 1], (64, 64), many), want[[5, 1]])
+    one.close()
+    many.close()
+
+
 def test_decoded_batch_feeds_k1_directly(tmp_path):
     """decode -> lh_warp_normalize with no host round trip: identity crop of the decoded images == ToTensor + Normalize."""
     from lighthand_b200 import ops
@@ -80,3 +100,8 @@ def test_wrong_size_is_reported(tmp_path):
     tsv = TSVFile(str(tmp_path / "frei_store.tsv"))
     with pytest.raises(LighthandError):
         JpegDecoder().decode(tsv.jpeg_batch([0]), (32, 32))
+    threaded = JpegDecoder(backend="hybrid", cpu_threads=4)      # the threaded mode checks inside its workers
+    with pytest.raises(LighthandError):
+        threaded.decode(tsv.jpeg_batch([0, 1, 2]), (32, 32))
+    assert threaded.decode(tsv.jpeg_batch([0, 1, 2]), (64, 64)).shape == (3, 64, 64, 3)      # and stays usable
+    threaded.close()
