@@ -323,7 +323,7 @@ int lh_color_jitter_normalize(const float* src, const lh_jitter_params* params, 
  * backend: nvJPEG's (DEFAULT, HYBRID = Huffman on the CPU, GPU_HYBRID = Huffman on the GPU, HARDWARE = the NVJPG engine).
  * cpu_threads: with HYBRID and cpu_threads > 1 the host Huffman stage runs on that many worker threads (nvJPEG's decoupled
  * API, one decoder state per thread, images handed out dynamically; the call returns when the batch is decoded); ignored
- * by the other backends.  The pixels do not depend on the thread count.
+ * by the other backends.  The pixels do not depend on the thread count.  One lh_jpeg serves one caller at a time.
  * Every bit-stream of a batch must have the size w x h (else LH_EINVAL).  The data / sizes arrays and the bit-streams
  * must stay valid until the stream has passed the call.
  * ------------------------------------------------------------------------------------------ */
