@@ -105,6 +105,31 @@ def main():
     rec("frei fused rgb_processing+Resize+Normalize+BGR (lh_frei_fused)",
         timeit(lambda i: ops.frei_fused(fimgs[i], desc, 224, sfl, mpx, (S, S), chan_order=ops.LH_CHAN_BGR, rot_index=rot, out=out_img), R),
         N * (224 * 224 * 3 + S * S * 12))
+    # the small entry points (latency-bound: microseconds per launch, bytes per second mean little)
+    from lighthand_b200.tools.dataset import color_jitter_params
+    torch.manual_seed(0)
+    jp = color_jitter_params([i % 2 == 0 for i in range(N)])
+    unit = torch.rand((N, 3, S, S), device=dev, generator=g)
+    d_jp = torch.from_numpy(np.frombuffer(bytes(jp), dtype=np.uint8).copy()).to(dev)
+    jws = torch.empty(N * ops._lib.LH_JITTER_PARTS, dtype=torch.float64, device=dev)
+    ms = ops._mean_std(ops.IMAGENET_MEAN, ops.IMAGENET_STD)
+    rec("color jitter + normalize (half of the batch augmented; parameters already on the device)",
+        timeit(lambda i: ops.check(lib.lh_color_jitter_normalize(unit.data_ptr(), d_jp.data_ptr(), N, S, S, ms, out_img.data_ptr(),
+                                                                  jws.data_ptr(), torch.cuda.current_stream().cuda_stream)), 1),
+        2 * N * 3 * S * S * 4)
+    jv = torch.cat([joints[0], torch.ones((N, J, 1), device=dev)], dim=2)
+    flip = (torch.arange(N, device=dev) % 2).to(torch.uint8)
+    rec("transform_joints", timeit(lambda i: ops.transform_joints(jv, M, (S, S), flip=flip, orig_w=S), 1), N * J * 24)
+    rec("bbox_diag", timeit(lambda i: ops.bbox_diag(jv), 1), N * J * 12)
+    xy = joints[1].contiguous()
+    counts, sums = ops.new_metric_state(dev)
+    rec("pck_epe_batch", timeit(lambda i: ops.pck_epe_batch(xy, joints[0], 0.2, "proportion", False, counts, sums), 1), N * J * 16)
+    thr = torch.arange(0, 31, dtype=torch.float64, device=dev)
+    hist = torch.zeros((1, 32), dtype=torch.int64, device=dev)
+    nv, na, sd = (torch.zeros(1, dtype=torch.int64, device=dev), torch.zeros(1, dtype=torch.int64, device=dev),
+                  torch.zeros(1, dtype=torch.float64, device=dev))
+    rec("pck_curve_accum (31 thresholds)", timeit(lambda i: ops.pck_curve_accum(xy, jv, thr, "mm", False, hist, nv, na, sd), 1),
+        N * J * 20)
     big_src = torch.empty((N, 3, S, S), device=dev)
     rec("torch_copy_201MB", timeit(lambda i: out_img.copy_(big_src), 1), 2 * N * 3 * S * S * 4)
     print(json.dumps(res, indent=1))
